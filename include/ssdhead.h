@@ -1,0 +1,151 @@
+/*
+ * ssdhead.h -- C ABI of libssdhead.so: the SSD300 detection-head hot path on B200 (sm_100a).
+ *
+ * The reference (rs1004/object-detection-torch2) has no FFI / plugin layer: its boundary for this path
+ * is the Python surface of src/model/ssd.py, src/utils.py and src/evaluate.py.  Each entry point below
+ * names the reference function (file:line under /root/reference) whose arithmetic it replaces; the
+ * Python mirror in object_detection_torch2_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the caller's current device unless marked "host";
+ *   - all tensors are dense row-major fp32 unless a stride argument says otherwise;
+ *   - the library never allocates, frees or synchronises: outputs and scratch are caller-owned, every
+ *     call only enqueues work on `stream` (a cudaStream_t passed as void*), so calls are CUDA-graph
+ *     capturable and thread-safe per stream;
+ *   - return value: 0 = OK, <0 = SSDH_E_* argument error, >0 = cudaError_t of a failed launch;
+ *     ssdh_last_error() returns a thread-local message for the last non-zero return;
+ *   - limits: 1 <= C <= 64 classes (incl. void at index 0), G <= 64 ground-truth rows per image,
+ *     one image's [P, 4+C] slab must fit the cluster's shared memory (P*(4+C)*4 <= ~1.7 MB).
+ */
+#ifndef SSDHEAD_H_
+#define SSDHEAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SSDH_API __attribute__((visibility("default")))
+#else
+#define SSDH_API
+#endif
+
+#define SSDH_VERSION 100
+
+#define SSDH_E_ARG       (-1)  /* null pointer / non-positive dimension                    */
+#define SSDH_E_LIMIT     (-2)  /* dimension above a documented limit (C, G, slab size)     */
+#define SSDH_E_ALIGN     (-3)  /* pointer not 16-byte aligned                              */
+#define SSDH_E_WORKSPACE (-4)  /* workspace missing or too small                           */
+
+typedef void* ssdh_stream_t;   /* cudaStream_t */
+
+/* Per-image by-products of the MultiBox loss (all written by ssdh_multibox_loss). */
+typedef struct ssdh_image_stats {
+  float loss;     /* inv_pos * sum over selected rows, src/model/ssd.py:227 before .mean()      */
+  float thr_pos;  /* (k_pos+1)-th largest positive CE, src/model/ssd.py:222                     */
+  float thr_neg;  /* (k_neg+1)-th largest negative CE, src/model/ssd.py:223                     */
+  int32_t pos_raw;  /* priors with >= 1 match, src/model/ssd.py:218                               */
+  int32_t k_pos;    /* after the 3:1 split, src/model/ssd.py:310-311                              */
+  int32_t k_neg;
+  int32_t pos_sel;  /* rows with ce_pos > thr_pos (can be < k_pos on ties)                        */
+  int32_t neg_sel;  /* rows with ce_neg > thr_neg                                                 */
+} ssdh_image_stats;
+
+SSDH_API int ssdh_version(void);
+SSDH_API const char* ssdh_last_error(void);
+
+/* Static facts about the loaded build and the current device (host out-params, may be NULL). */
+SSDH_API int ssdh_device_info(int* sm_count, int* max_smem_optin, int* loss_cluster_size, int* loss_max_active_clusters);
+
+/* P1  SSD._get_default_bboxes, src/model/ssd.py:108-133.  out: [8732, 4] = [cx, cy, w, h]. */
+SSDH_API int ssdh_default_boxes(float* out, ssdh_stream_t stream);
+#define SSDH_NUM_PRIORS 8732
+
+/* L1  SSD._match, src/model/ssd.py:231-250 (IoU > thr, no forcing).
+ * gt: [N, G, gt_row_stride] rows, columns 0..3 read.  priors: [P, 4].
+ * match_bits [N, P] u64 (bit g = prior matches gt g)            -- may be NULL
+ * match_mask [N, P, G] u8 0/1, the reference's bool layout      -- may be NULL
+ * best_gt [N, P] i32 / best_iou [N, P]: arg-max IoU over gt per prior (first max), may be NULL
+ * best_prior [N, G] i32 / best_prior_iou [N, G]: arg-max IoU over priors per gt (lowest index on
+ * ties), the hook for best-prior forcing (north_star extension), may be NULL. */
+SSDH_API int ssdh_match(const float* gt, int gt_row_stride, int N, int G, const float* priors, int P, float thr,
+               uint64_t* match_bits, uint8_t* match_mask, int32_t* best_gt, float* best_iou,
+               int32_t* best_prior, float* best_prior_iou, ssdh_stream_t stream);
+
+/* L2  SSD._calc_delta, src/model/ssd.py:252-272.  out: [N, P, G, 4]. */
+SSDH_API int ssdh_encode(const float* gt, int gt_row_stride, int N, int G, const float* priors, int P, float* out,
+                ssdh_stream_t stream);
+
+/* L3  SSD._smooth_l1, src/model/ssd.py:274-283, elementwise over n floats. */
+SSDH_API int ssdh_smooth_l1(const float* x, float* out, size_t n, ssdh_stream_t stream);
+
+/* L4  SSD._softmax_cross_entropy, src/model/ssd.py:285-298.
+ * pr: [N, P, pr_row_stride] with C logits from column 0; gt: [N, G, gt_row_stride] with C weights from
+ * column 0; out: [N, P, G]. */
+SSDH_API int ssdh_softmax_cross_entropy(const float* pr, int pr_row_stride, const float* gt, int gt_row_stride,
+                               int N, int P, int G, int C, float* out, ssdh_stream_t stream);
+
+/* L5  SSD._split_pos_neg, src/model/ssd.py:300-311 (int64 in / out, n entries). */
+SSDH_API int ssdh_split_pos_neg(const int64_t* pos, const int64_t* neg, int64_t* pos_out, int64_t* neg_out, int n,
+                       ssdh_stream_t stream);
+
+/* L6  SSD._k_plus_1_th_value, src/model/ssd.py:313-328, batched: values [rows, len], k [rows] (device i64),
+ * out [rows] = (k+1)-th largest of each row (k = 0 -> max).  Radix select, no sort. */
+SSDH_API int ssdh_kplus1_value(const float* values, int rows, int len, const int64_t* k, float* out, ssdh_stream_t stream);
+
+/* L1-L7 fused  SSD.loss, src/model/ssd.py:181-229, forward and gradient in one launch.
+ * outputs [N, P, 4+C], targets [N, G, 4+C], priors [P, 4]; `a` = localisation weight; thr = match IoU.
+ * n_global: the divisor of the batch mean (= N on one GPU, the global batch when images are sharded).
+ * loss [1]: sum_i stats[i].loss / n_global.   grad [N, P, 4+C] = d loss / d outputs, or NULL (forward only).
+ * stats [N] or NULL.  ws: ssdh_multibox_loss_workspace_bytes() bytes, ZEROED ONCE by the caller before the
+ * first call (the kernel leaves it zeroed). */
+SSDH_API size_t ssdh_multibox_loss_workspace_bytes(int N, int P, int C, int G);
+SSDH_API int ssdh_multibox_loss(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
+                       float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
+                       void* ws, size_t ws_bytes, ssdh_stream_t stream);
+
+/* grad *= *scale (device scalar), skipped entirely when *scale == 1: the autograd chain-rule hook. */
+SSDH_API int ssdh_scale_inplace(float* x, size_t n, const float* scale, ssdh_stream_t stream);
+
+/* I1  calc_coordicate, src/utils.py:19-40.  pr: [N, P, pr_row_stride] (cols 0..3), out: [N, P, 4]. */
+SSDH_API int ssdh_decode(const float* pr, int pr_row_stride, const float* priors, int N, int P, float* out, ssdh_stream_t stream);
+
+/* I2  calc_score, src/utils.py:43-55.  pr: [N, P, pr_row_stride] with C logits from column 4; out: [N, P, C]. */
+SSDH_API int ssdh_score(const float* pr, int pr_row_stride, int N, int P, int C, float* out, ssdh_stream_t stream);
+
+/* I3  calc_iou, src/utils.py:58-77.  t: [N, T, t_row_stride], s: [N, S, s_row_stride] (cols 0..3); out [N, T, S]. */
+SSDH_API int ssdh_iou(const float* t, int t_row_stride, int T, const float* s, int s_row_stride, int S, int N, float* out,
+             ssdh_stream_t stream);
+
+/* I4  non_maximum_suppression, src/utils.py:80-116, in place on outputs [N, P, 4+C] (decoded + scored).
+ * Reference behaviour: score_thr = 0, top_k = 0 (off), per_class = 0, iou_thr = 0.5.
+ * order [N, P] i32 / order_cnt [N]: candidate rows by descending best non-void score (stable) -- may be NULL
+ * keep  [N, P] i32 / keep_cnt  [N]: kept rows in that order                                  -- may be NULL
+ * Score columns of every row that is not kept are set to 0; box columns are untouched. */
+SSDH_API size_t ssdh_nms_workspace_bytes(int N, int P, int C);
+SSDH_API int ssdh_nms(float* outputs, int N, int P, int C, float iou_thr, float score_thr, int top_k, int per_class,
+             int32_t* order, int32_t* order_cnt, int32_t* keep, int32_t* keep_cnt,
+             void* ws, size_t ws_bytes, ssdh_stream_t stream);
+
+/* I1+I2+I4 fused: the three calls at src/evaluate.py:129-131 / src/inference.py:67-69 in one pass over
+ * outputs [N, P, 4+C] (raw head output in, decoded boxes + NMS-masked scores out, in place). */
+SSDH_API int ssdh_postprocess(float* outputs, const float* priors, int N, int P, int C, float iou_thr, float score_thr,
+                     int top_k, int per_class, int32_t* order, int32_t* order_cnt, int32_t* keep, int32_t* keep_cnt,
+                     void* ws, size_t ws_bytes, ssdh_stream_t stream);
+
+/* E1+E2  TP/FP assignment, src/evaluate.py:31-42 and :132-151, accumulated as sufficient statistics.
+ * outputs [N, P, 4+C] after NMS, gts [N, G, 4+C].  tallies [C-1, 3] i64 += {TP, detections, ground truths}
+ * per class (atomic adds: zero it before the first batch).  tp_flags [N, P] u8 or NULL: 1 = true positive,
+ * 0 = false positive, 255 = row is not a detection.  Rows must carry at most one positive class score
+ * (always true after calc_score). */
+SSDH_API size_t ssdh_eval_workspace_bytes(int N, int P, int C, int G);
+SSDH_API int ssdh_eval_accumulate(const float* outputs, const float* gts, int N, int P, int C, int G, float iou_thr,
+                         int64_t* tallies, uint8_t* tp_flags, void* ws, size_t ws_bytes, ssdh_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSDHEAD_H_ */

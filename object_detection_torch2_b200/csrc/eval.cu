@@ -1,0 +1,176 @@
+// E1 + E2: per-class TP/FP assignment accumulated as integer tallies.  Replaces get_order and the loop body of
+// the evaluation script (reference src/evaluate.py:31-42 and :132-151).
+//
+// The reference sorts the detections of a class by score and lets each one claim its arg-max-IoU ground truth
+// (valid when IoU > 0.5); a detection is a true positive iff it is the FIRST claimant of that box
+// (evaluate.py:146-148).  "First in descending score order, ties by lower row" is a minimum over the key
+// (~score_bits, row), so no sort is needed: one atomicMin per valid detection, then one compare.
+// The reference's AP (evaluate.py:45-67) reduces to TP / #gt, so {TP, detections, gt} per class
+// are sufficient statistics and sum exactly across images and GPUs.
+#include "common.cuh"
+
+namespace ssdh {
+
+constexpr int kEvalThreads = 512;
+
+struct EvalParams {
+  const float* outputs;
+  const float* gts;
+  int P, C, G;
+  ThrBand band;
+  unsigned long long* tallies;   // [C-1, 3]
+  uint8_t* tp_flags;             // [N, P] or NULL
+  int* status;                   // workspace: set to 1 if an image had more than P detections
+};
+
+struct Det {
+  float score;
+  uint16_t row;
+  uint8_t cls;      // 0-based non-void class
+  uint8_t best_g;   // 255 = no valid claim
+};
+
+__global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = blockIdx.x, P = p.P, C = p.C, G = p.G, row = 4 + C, NC = C - 1;
+  const int tid = threadIdx.x;
+  // layout
+  unsigned long long* claim = reinterpret_cast<unsigned long long*>(smem_raw);          // [NC][G]
+  Corners* gt_box = reinterpret_cast<Corners*>(claim + static_cast<size_t>(NC) * G);     // [G]
+  float* gt_val = reinterpret_cast<float*>(gt_box + G);                                  // [NC][G] class column values
+  uint8_t* gt_order = reinterpret_cast<uint8_t*>(gt_val + static_cast<size_t>(NC) * G);  // [NC][G]
+  int* gt_cnt = reinterpret_cast<int*>(gt_order + ((static_cast<size_t>(NC) * G + 3) & ~static_cast<size_t>(3)));  // [NC]
+  int* tp_cnt = gt_cnt + NC;
+  int* det_cnt = tp_cnt + NC;
+  int* n_det = det_cnt + NC;
+  Det* dets = reinterpret_cast<Det*>(n_det + 4);                                         // [P]
+
+  const float* img = p.outputs + static_cast<size_t>(n) * P * row;
+  const float* gimg = p.gts + static_cast<size_t>(n) * G * row;
+
+  for (int i = tid; i < NC * G; i += kEvalThreads) {
+    claim[i] = ~0ull;
+    gt_val[i] = gimg[static_cast<size_t>(i % G) * row + 5 + i / G];
+  }
+  for (int g = tid; g < G; g += kEvalThreads) {
+    const float* r = gimg + static_cast<size_t>(g) * row;
+    gt_box[g] = make_corners(r[0], r[1], r[2], r[3]);
+  }
+  for (int c = tid; c < NC; c += kEvalThreads) { tp_cnt[c] = 0; det_cnt[c] = 0; }
+  if (tid == 0) *n_det = 0;
+  if (p.tp_flags)
+    for (int i = tid; i < P; i += kEvalThreads) p.tp_flags[static_cast<size_t>(n) * P + i] = 255;
+  __syncthreads();
+
+  // get_order on the ground truth (evaluate.py:41-42): rows with a positive class column, by that value
+  // descending, ties by lower row.  G <= 64: insertion by one thread per class.
+  for (int c = tid; c < NC; c += kEvalThreads) {
+    int cnt = 0;
+    for (int g = 0; g < G; ++g) {
+      const float v = gt_val[c * G + g];
+      if (!(v > 0.0f)) continue;
+      int j = cnt++;
+      while (j > 0 && gt_val[c * G + gt_order[c * G + j - 1]] < v) { gt_order[c * G + j] = gt_order[c * G + j - 1]; --j; }
+      gt_order[c * G + j] = static_cast<uint8_t>(g);
+    }
+    gt_cnt[c] = cnt;
+  }
+
+  // detections: every positive entry of the score columns 5.. (coalesced flat scan of the image slab)
+  const int total = P * row;
+  for (int i = tid; i < total; i += kEvalThreads) {
+    const float v = img[i];
+    if (!(v > 0.0f)) continue;
+    const int r = i / row, c = i - r * row;
+    if (c < 5) continue;
+    const int slot = atomicAdd(n_det, 1);
+    if (slot < P) {
+      Det d;
+      d.score = v; d.row = static_cast<uint16_t>(r); d.cls = static_cast<uint8_t>(c - 5); d.best_g = 255;
+      dets[slot] = d;
+    }
+  }
+  __syncthreads();
+  int D = *n_det;
+  if (D > P) {
+    if (tid == 0) atomicExch(p.status, 1);
+    D = P;
+  }
+
+  for (int i = tid; i < D; i += kEvalThreads) {
+    Det d = dets[i];
+    const int c = d.cls;
+    const float* b = img + static_cast<size_t>(d.row) * row;
+    const Corners me = make_corners(b[0], b[1], b[2], b[3]);
+    const int cnt = gt_cnt[c];
+    float best = -INFINITY;
+    int bg = -1;
+    for (int j = 0; j < cnt; ++j) {                       // arg-max over the class's gt in get_order order, first max wins
+      const int g = gt_order[c * G + j];
+      const float v = iou_value(me, gt_box[g]);
+      if (v > best) { best = v; bg = g; }
+    }
+    if (bg >= 0 && best > p.band.thr) {                   // evaluate.py:147
+      const unsigned long long key = (static_cast<unsigned long long>(~float_key(d.score)) << 32) | d.row;
+      atomicMin(&claim[c * G + bg], key);
+      dets[i].best_g = static_cast<uint8_t>(bg);
+    }
+    atomicAdd(&det_cnt[c], 1);
+  }
+  __syncthreads();
+  for (int i = tid; i < D; i += kEvalThreads) {
+    const Det d = dets[i];
+    bool tp = false;
+    if (d.best_g != 255) {
+      const unsigned long long key = (static_cast<unsigned long long>(~float_key(d.score)) << 32) | d.row;
+      tp = claim[d.cls * G + d.best_g] == key;            // first claimant in score order, evaluate.py:148
+    }
+    if (tp) atomicAdd(&tp_cnt[d.cls], 1);
+    if (p.tp_flags) p.tp_flags[static_cast<size_t>(n) * P + d.row] = tp ? 1 : 0;
+  }
+  __syncthreads();
+  for (int c = tid; c < NC; c += kEvalThreads) {
+    if (tp_cnt[c]) atomicAdd(&p.tallies[c * 3 + 0], static_cast<unsigned long long>(tp_cnt[c]));
+    if (det_cnt[c]) atomicAdd(&p.tallies[c * 3 + 1], static_cast<unsigned long long>(det_cnt[c]));
+    if (gt_cnt[c]) atomicAdd(&p.tallies[c * 3 + 2], static_cast<unsigned long long>(gt_cnt[c]));
+  }
+}
+
+static size_t eval_smem_bytes(int P, int C, int G) {
+  const size_t NC = C - 1;
+  size_t b = NC * G * 8 + static_cast<size_t>(G) * sizeof(Corners) + NC * G * 4 + ((NC * G + 3) & ~static_cast<size_t>(3)) + (3 * NC + 4) * 4;
+  b = (b + 15) & ~static_cast<size_t>(15);
+  return b + static_cast<size_t>(P) * sizeof(Det) + 16;
+}
+
+}  // namespace ssdh
+
+using namespace ssdh;
+
+extern "C" size_t ssdh_eval_workspace_bytes(int N, int P, int C, int G) {
+  (void)N; (void)P; (void)C; (void)G;
+  return 256;
+}
+
+extern "C" int ssdh_eval_accumulate(const float* outputs, const float* gts, int N, int P, int C, int G, float iou_thr,
+                                    int64_t* tallies, uint8_t* tp_flags, void* ws, size_t ws_bytes, ssdh_stream_t stream) {
+  if (!outputs || !tallies || N <= 0 || P <= 0 || C <= 1 || G < 0 || (G > 0 && !gts)) { set_error("ssdh_eval_accumulate: bad argument"); return SSDH_E_ARG; }
+  if (C > kMaxClasses || G > kMaxGT || P > 65535) { set_error("ssdh_eval_accumulate: limits are C <= %d, G <= %d, P <= 65535", kMaxClasses, kMaxGT); return SSDH_E_LIMIT; }
+  if (!ws || ws_bytes < ssdh_eval_workspace_bytes(N, P, C, G)) { set_error("ssdh_eval_accumulate: workspace too small"); return SSDH_E_WORKSPACE; }
+  const size_t smem = eval_smem_bytes(P, C, G);
+  if (smem > 227 * 1024) { set_error("ssdh_eval_accumulate: needs %zu bytes of shared memory", smem); return SSDH_E_LIMIT; }
+  static bool cfg = false;
+  if (!cfg) {
+    cudaError_t e = cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("ssdh_eval_accumulate: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+    cfg = true;
+  }
+  EvalParams p;
+  p.outputs = outputs; p.gts = gts; p.P = P; p.C = C; p.G = G;
+  p.band = make_band(iou_thr);
+  p.tallies = reinterpret_cast<unsigned long long*>(tallies);
+  p.tp_flags = tp_flags;
+  p.status = reinterpret_cast<int*>(ws);
+  eval_kernel<<<N, kEvalThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return cuda_status("ssdh_eval_accumulate");
+}

@@ -1,0 +1,567 @@
+// Inference-time post-processing: decode (I1), score (I2), pairwise IoU (I3), greedy NMS (I4) and the fused
+// decode+score+NMS pass.  Replaces calc_coordicate / calc_score / calc_iou / non_maximum_suppression
+// (reference src/utils.py:19-116) as they are chained at src/evaluate.py:129-131 and src/inference.py:67-69.
+//
+// NMS decomposition: one CTA of 1024 threads per image.
+//   A. candidate keys (best non-void score, src/utils.py:99) are compacted in row order,
+//   B. block-wide LSD radix sort (8-bit digits, warp match_any ranking) -> descending score, ties by lower row
+//      (the stable order; the reference's torch.sort is unstable on ties),
+//   C. tiled greedy suppression: every candidate of a 1024-wide tile is tested against the kept boxes held
+//      in shared memory (broadcast reads), then the tile is resolved warp by warp with ballots; IoU uses the
+//      same fp32 operation sequence as src/utils.py:74-77 so keep lists are bit-identical,
+//   D. score columns of rows that were not kept are zeroed (src/utils.py:114).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ssdh {
+
+// ------------------------------------------------------------------------------------------------
+// I1 / I2 row math shared by the stand-alone kernels and the fused pass (bitwise identical results)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 decode_row(float p0, float p1, float p2, float p3, const float4 d) {
+  float4 o;
+  o.x = __fadd_rn(__fmul_rn(d.z, p0), d.x);        // src/utils.py:35
+  o.y = __fadd_rn(__fmul_rn(d.w, p1), d.y);        // src/utils.py:36
+  o.z = __fmul_rn(d.z, expf(p2));                  // src/utils.py:37
+  o.w = __fmul_rn(d.w, expf(p3));                  // src/utils.py:38
+  return o;
+}
+
+// softmax value at the arg-max class (first max wins) -- the only non-zero of the row, src/utils.py:54-55
+template <typename Load>
+__device__ __forceinline__ float best_score(Load logit, int C, int& best) {
+  float mx = logit(0);
+  best = 0;
+  for (int c = 1; c < C; ++c) {
+    const float v = logit(c);
+    if (v > mx) { mx = v; best = c; }
+  }
+  float sum = 0.0f;
+  for (int c = 0; c < C; ++c) sum += expf(logit(c) - mx);
+  return __fdiv_rn(1.0f, sum);
+}
+
+__global__ void __launch_bounds__(256)
+decode_kernel(const float* __restrict__ pr, int stride, const float4* __restrict__ priors, int P, float4* __restrict__ out, size_t rows) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float* r = pr + i * stride;
+  out[i] = decode_row(r[0], r[1], r[2], r[3], priors[i % P]);
+}
+
+__global__ void __launch_bounds__(256)
+score_kernel(const float* __restrict__ pr, int stride, int C, float* __restrict__ out, size_t rows) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float* r = pr + i * stride + 4;
+  int best;
+  const float s = best_score([&](int c) { return r[c]; }, C, best);
+  float* o = out + i * C;
+  for (int c = 0; c < C; ++c) o[c] = (c == best) ? s : 0.0f;
+}
+
+// I3  src/utils.py:58-77
+__global__ void __launch_bounds__(256)
+iou_kernel(const float* __restrict__ t, int t_stride, int T, const float* __restrict__ s, int s_stride, int S,
+           float* __restrict__ out, size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // over N*T*S
+  if (i >= total) return;
+  const int si = static_cast<int>(i % S);
+  const size_t nt = i / S;
+  const size_t n = nt / T;
+  const float* a = t + nt * t_stride;
+  const float* b = s + (n * S + si) * s_stride;
+  out[i] = iou_value(make_corners(a[0], a[1], a[2], a[3]), make_corners(b[0], b[1], b[2], b[3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused pass, kernel 1: decode + score for every row, one read and one write of the slab.
+// Writes decoded boxes, ZERO score columns (the NMS kernel scatters the kept scores back) and the
+// per-row candidate key / class used by the sort.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileRows = 256;
+
+__global__ void __launch_bounds__(kTileRows)
+decode_score_kernel(float* __restrict__ outputs, const float4* __restrict__ priors, int P, int C, size_t total_rows,
+                    float* __restrict__ cand_key, uint8_t* __restrict__ cand_cls, int vec_ok) {
+  extern __shared__ __align__(16) float tile[];
+  const int row = 4 + C;
+  const size_t r0 = static_cast<size_t>(blockIdx.x) * kTileRows;
+  const int rows = static_cast<int>(min(static_cast<size_t>(kTileRows), total_rows - r0));
+  float* base = outputs + r0 * row;
+  const int nfl = rows * row;
+  if (vec_ok && (nfl & 3) == 0) {
+    const float4* b4 = reinterpret_cast<const float4*>(base);
+    float4* t4 = reinterpret_cast<float4*>(tile);
+    for (int i = threadIdx.x; i < nfl / 4; i += kTileRows) t4[i] = __ldcs(b4 + i);
+  } else {
+    for (int i = threadIdx.x; i < nfl; i += kTileRows) tile[i] = base[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < rows) {
+    float* r = tile + threadIdx.x * row;
+    const size_t grow = r0 + threadIdx.x;
+    const float4 box = decode_row(r[0], r[1], r[2], r[3], priors[grow % P]);
+    int best;
+    const float s = best_score([&](int c) { return r[4 + c]; }, C, best);
+    r[0] = box.x; r[1] = box.y; r[2] = box.z; r[3] = box.w;
+    for (int c = 0; c < C; ++c) r[4 + c] = 0.0f;
+    cand_key[grow] = best != 0 ? s : 0.0f;          // max over non-void columns, src/utils.py:99
+    cand_cls[grow] = static_cast<uint8_t>(best);
+  }
+  __syncthreads();
+  if (vec_ok && (nfl & 3) == 0) {
+    float4* b4 = reinterpret_cast<float4*>(base);
+    const float4* t4 = reinterpret_cast<const float4*>(tile);
+    for (int i = threadIdx.x; i < nfl / 4; i += kTileRows) b4[i] = t4[i];
+  } else {
+    for (int i = threadIdx.x; i < nfl; i += kTileRows) base[i] = tile[i];
+  }
+}
+
+// Stand-alone NMS, kernel 1: candidate key / class from already scored rows (general rows: any number of
+// positive classes; key = max over columns 5.., class = its arg-max, first max wins).
+__global__ void __launch_bounds__(256)
+candidate_kernel(const float* __restrict__ outputs, int C, size_t total_rows, float* __restrict__ cand_key,
+                 uint8_t* __restrict__ cand_cls) {
+  const int row = 4 + C;
+  const int lane = threadIdx.x & 31;
+  const size_t warp_global = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+  // one warp per row: lanes read the row's score columns (coalesced 4*(C-1) bytes), shuffle arg-max
+  for (size_t r = warp_global; r < total_rows; r += n_warps) {
+    const float* p = outputs + r * row + 5;
+    float best = -INFINITY;
+    int bc = 0x7fffffff;
+    for (int c = lane; c < C - 1; c += 32) {
+      const float v = p[c];
+      if (v > best) { best = v; bc = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (ov > best || (ov == best && oc < bc)) { best = ov; bc = oc; }
+    }
+    if (lane == 0) {
+      cand_key[r] = (C > 1) ? best : 0.0f;
+      cand_cls[r] = static_cast<uint8_t>(C > 1 ? bc + 1 : 0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NMS kernel: one CTA per image
+// ------------------------------------------------------------------------------------------------
+constexpr int kNmsThreads = 1024;
+constexpr int kNmsWarps = 32;
+constexpr int kMaxRounds = 10;                 // candidates per thread in the sort -> P <= 10240
+
+struct NmsParams {
+  float* outputs;
+  int P, C;
+  const float* cand_key;      // [N, P]
+  const uint8_t* cand_cls;    // [N, P]
+  ThrBand band;
+  float score_thr;
+  int top_k, per_class, scatter;   // scatter = 1: fused pass (write kept scores), 0: zero rows not kept
+  int32_t* order;             // [N, P] (workspace or user)
+  int32_t* order_cnt;         // [N] or NULL
+  int32_t* keep;              // [N, P] (workspace or user)
+  int32_t* keep_cnt;          // [N] or NULL
+};
+
+struct NmsShared {
+  int warp_total[kNmsWarps];
+  int warp_alive[kNmsWarps];
+  int part[4][256];
+  int digit_base[256];
+  int n_cand, kept, uniform_digit, stop;
+};
+
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = blockIdx.x, P = p.P, row = 4 + p.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  // layout: [NmsShared][keep bitmap: P bits][union{ sort buffers | kept list }]
+  NmsShared& sh = *reinterpret_cast<NmsShared*>(smem_raw);
+  size_t off = (sizeof(NmsShared) + 15) & ~static_cast<size_t>(15);
+  uint32_t* keep_bits = reinterpret_cast<uint32_t*>(smem_raw + off);
+  const int bit_words = (P + 31) / 32;
+  off += (static_cast<size_t>(bit_words) * 4 + 15) & ~static_cast<size_t>(15);
+  unsigned char* region = smem_raw + off;
+  const size_t Pp = (static_cast<size_t>(P) + 15) & ~static_cast<size_t>(15);
+  // sort view
+  uint32_t* keys_a = reinterpret_cast<uint32_t*>(region);
+  uint32_t* keys_b = keys_a + Pp;
+  uint16_t* idx_a = reinterpret_cast<uint16_t*>(keys_b + Pp);
+  uint16_t* idx_b = idx_a + Pp;
+  uint16_t* whist = idx_b + Pp;                 // [32 warps][256 digits]
+  // kept-list view (aliases the sort buffers, used after the order has been written to global memory)
+  float4* k_box = reinterpret_cast<float4*>(region);          // x1, x2, y1, y2
+  float* k_area = reinterpret_cast<float*>(k_box + Pp);
+  uint8_t* k_cls = reinterpret_cast<uint8_t*>(k_area + Pp);
+
+  const float* key_in = p.cand_key + static_cast<size_t>(n) * P;
+  const uint8_t* cls_in = p.cand_cls + static_cast<size_t>(n) * P;
+  int32_t* order = p.order + static_cast<size_t>(n) * P;
+  int32_t* keep = p.keep + static_cast<size_t>(n) * P;
+  float* img = p.outputs + static_cast<size_t>(n) * P * row;
+
+  if (tid == 0) { sh.n_cand = 0; sh.kept = 0; sh.stop = 0; }
+  for (int i = tid; i < bit_words; i += kNmsThreads) keep_bits[i] = 0u;
+  __syncthreads();
+
+  // ---- A. compaction in row order ---------------------------------------------------------------------
+  for (int base = 0; base < P; base += kNmsThreads) {
+    const int r = base + tid;
+    float key = 0.0f;
+    if (r < P) key = key_in[r];
+    const bool cand = (r < P) && (key > p.score_thr);
+    const uint32_t ballot = __ballot_sync(0xffffffffu, cand);
+    if (lane == 0) sh.warp_total[warp] = __popc(ballot);
+    __syncthreads();
+    int before = sh.n_cand;
+    for (int w = 0; w < warp; ++w) before += sh.warp_total[w];
+    if (cand) {
+      const int pos = before + __popc(ballot & lt_mask);
+      keys_a[pos] = ~float_key(key);              // ascending sort of ~key = descending score
+      idx_a[pos] = static_cast<uint16_t>(r);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < kNmsWarps; ++w) t += sh.warp_total[w];
+      sh.n_cand += t;
+    }
+    __syncthreads();
+  }
+  const int K = sh.n_cand;
+
+  // ---- B. stable LSD radix sort of (key, idx) -------------------------------------------------------------
+  {
+    const int seg = ((K + kNmsWarps * 32 - 1) / (kNmsWarps * 32)) * 32;     // per-warp segment, multiple of 32
+    const int rounds = seg / 32;                                              // <= kMaxRounds
+    uint32_t* kin = keys_a; uint32_t* kout = keys_b;
+    uint16_t* iin = idx_a;  uint16_t* iout = idx_b;
+    for (int pass = 0; pass < 4 && K > 1; ++pass) {
+      const int shift = 8 * pass;
+      for (int i = tid; i < kNmsWarps * 256 / 2; i += kNmsThreads) reinterpret_cast<uint32_t*>(whist)[i] = 0u;
+      __syncthreads();
+      int loc[kMaxRounds];
+      uint16_t* my_hist = whist + warp * 256;
+#pragma unroll
+      for (int r = 0; r < kMaxRounds; ++r) {
+        loc[r] = 0;
+        if (r < rounds) {
+          const int i = warp * seg + r * 32 + lane;
+          const bool act = i < K;
+          const uint32_t d = act ? ((kin[i] >> shift) & 255u) : 0xffffffffu;
+          const uint32_t peers = __match_any_sync(0xffffffffu, d);
+          int prev = 0;
+          if (act) prev = my_hist[d];
+          __syncwarp();
+          if (act && lane == __ffs(peers) - 1) my_hist[d] = static_cast<uint16_t>(prev + __popc(peers));
+          __syncwarp();
+          loc[r] = prev + __popc(peers & lt_mask);
+        }
+      }
+      __syncthreads();
+      // exclusive scan over (digit major, warp minor)
+      {
+        const int d = tid & 255, q = tid >> 8;      // q handles warps [8q, 8q+8)
+        int s = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += whist[(8 * q + w) * 256 + d];
+        sh.part[q][d] = s;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        int t[8], s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int d = lane * 8 + j;
+          t[j] = sh.part[0][d] + sh.part[1][d] + sh.part[2][d] + sh.part[3][d];
+          s += t[j];
+        }
+        const int incl = warp_incl_scan(s, lane);
+        int run = incl - s;
+        bool uni = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sh.digit_base[lane * 8 + j] = run;
+          run += t[j];
+          uni |= (t[j] == K);
+        }
+        const uint32_t any_uni = __ballot_sync(0xffffffffu, uni);
+        if (lane == 0) sh.uniform_digit = any_uni != 0u;
+      }
+      __syncthreads();
+      if (sh.uniform_digit) { __syncthreads(); continue; }     // every key has the same digit: nothing moves
+      {
+        const int d = tid & 255, q = tid >> 8;
+        int run = sh.digit_base[d];
+        for (int qq = 0; qq < q; ++qq) run += sh.part[qq][d];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const int c = whist[(8 * q + w) * 256 + d];
+          whist[(8 * q + w) * 256 + d] = static_cast<uint16_t>(run);
+          run += c;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kMaxRounds; ++r) {
+        if (r < rounds) {
+          const int i = warp * seg + r * 32 + lane;
+          if (i < K) {
+            const uint32_t key = kin[i];
+            const int pos = my_hist[(key >> shift) & 255u] + loc[r];
+            kout[pos] = key;
+            iout[pos] = iin[i];
+          }
+        }
+      }
+      __syncthreads();
+      uint32_t* tk = kin; kin = kout; kout = tk;
+      uint16_t* ti = iin; iin = iout; iout = ti;
+    }
+    // the sorted order leaves shared memory here; the kept list takes over the region
+    for (int i = tid; i < K; i += kNmsThreads) order[i] = iin[i];
+    for (int i = K + tid; i < P; i += kNmsThreads) order[i] = -1;
+    __syncthreads();
+  }
+
+  // ---- C. greedy suppression -----------------------------------------------------------------------------
+  const ThrBand band = p.band;
+  const int limit = p.top_k > 0 ? p.top_k : 0x7fffffff;
+  for (int base = 0; base < K; base += kNmsThreads) {
+    if (sh.stop) break;
+    const int i = base + tid;
+    bool alive = i < K;
+    int my_row = 0, my_cls = 0;
+    Corners me = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (alive) {
+      my_row = order[i];
+      const float* b = img + static_cast<size_t>(my_row) * row;
+      me = make_corners(b[0], b[1], b[2], b[3]);
+      if (p.per_class) my_cls = cls_in[my_row];
+    }
+    const int kept_before = sh.kept;
+    // (1) against everything kept by earlier tiles: broadcast reads of the kept list
+    for (int j0 = 0; j0 < kept_before; j0 += 32) {
+      if (!__any_sync(0xffffffffu, alive)) break;
+      const int j1 = min(j0 + 32, kept_before);
+      for (int j = j0; j < j1; ++j) {
+        const float4 kb = k_box[j];
+        Corners o;
+        o.x1 = kb.x; o.x2 = kb.y; o.y1 = kb.z; o.y2 = kb.w; o.area = k_area[j];
+        bool hit = iou_gt(o, me, band);
+        if (p.per_class) hit = hit && (k_cls[j] == my_cls);
+        alive = alive && !hit;
+      }
+    }
+    {
+      const uint32_t ballot = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0) sh.warp_alive[warp] = static_cast<int>(ballot);
+    }
+    __syncthreads();
+    // (2) resolve the tile warp by warp, in score order
+    for (int w = 0; w < kNmsWarps; ++w) {
+      if (sh.warp_alive[w] == 0) continue;            // block-uniform
+      if (sh.stop) break;                             // block-uniform (set before a barrier)
+      if (warp == w) {
+        const int kept_now = sh.kept;
+        for (int j = kept_before; j < kept_now; ++j) {            // boxes kept by earlier warps of this tile
+          const float4 kb = k_box[j];
+          Corners o;
+          o.x1 = kb.x; o.x2 = kb.y; o.y1 = kb.z; o.y2 = kb.w; o.area = k_area[j];
+          bool hit = iou_gt(o, me, band);
+          if (p.per_class) hit = hit && (k_cls[j] == my_cls);
+          alive = alive && !hit;
+        }
+        uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
+        uint32_t todo = alive_mask;
+        while (todo) {
+          const int j = __ffs(todo) - 1;
+          todo &= todo - 1;
+          Corners o;
+          o.x1 = __shfl_sync(0xffffffffu, me.x1, j);
+          o.x2 = __shfl_sync(0xffffffffu, me.x2, j);
+          o.y1 = __shfl_sync(0xffffffffu, me.y1, j);
+          o.y2 = __shfl_sync(0xffffffffu, me.y2, j);
+          o.area = __shfl_sync(0xffffffffu, me.area, j);
+          const int ocls = __shfl_sync(0xffffffffu, my_cls, j);
+          if (alive && lane > j) {
+            bool hit = iou_gt(o, me, band);
+            if (p.per_class) hit = hit && (ocls == my_cls);
+            alive = !hit;
+          }
+          alive_mask = __ballot_sync(0xffffffffu, alive);
+          todo &= alive_mask;
+        }
+        const int pos = kept_now + __popc(alive_mask & lt_mask);
+        if (alive && pos < limit) {
+          k_box[pos] = make_float4(me.x1, me.x2, me.y1, me.y2);
+          k_area[pos] = me.area;
+          k_cls[pos] = static_cast<uint8_t>(my_cls);
+          keep[pos] = my_row;
+          atomicOr(&keep_bits[my_row >> 5], 1u << (my_row & 31));
+        }
+        if (lane == 0) {
+          const int total = min(kept_now + __popc(alive_mask), limit);
+          sh.kept = total;
+          if (total >= limit) sh.stop = 1;
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const int kept = sh.kept;
+  for (int i = kept + tid; i < P; i += kNmsThreads) keep[i] = -1;
+  if (tid == 0) {
+    if (p.keep_cnt) p.keep_cnt[n] = kept;
+    if (p.order_cnt) p.order_cnt[n] = K;
+  }
+
+  // ---- D. apply ------------------------------------------------------------------------------------------
+  if (p.scatter) {
+    for (int j = tid; j < kept; j += kNmsThreads) {
+      const int r = keep[j];
+      img[static_cast<size_t>(r) * row + 4 + cls_in[r]] = key_in[r];
+    }
+  } else {
+    // outputs[:, :, 4:] *= mask (src/utils.py:114): rows not kept lose every score, void column included
+    for (int r = warp; r < P; r += kNmsWarps) {
+      if ((keep_bits[r >> 5] >> (r & 31)) & 1u) continue;
+      float* dst = img + static_cast<size_t>(r) * row + 4;
+      for (int c = lane; c < p.C; c += 32) dst[c] = 0.0f;
+    }
+  }
+}
+
+static size_t nms_smem_bytes(int P) {
+  const size_t Pp = (static_cast<size_t>(P) + 15) & ~static_cast<size_t>(15);
+  const size_t head = ((sizeof(NmsShared) + 15) & ~static_cast<size_t>(15)) + ((static_cast<size_t>((P + 31) / 32) * 4 + 15) & ~static_cast<size_t>(15));
+  const size_t sort_bytes = Pp * (4 + 4 + 2 + 2) + kNmsWarps * 256 * 2;
+  const size_t kept_bytes = Pp * (16 + 4 + 1);
+  return head + (sort_bytes > kept_bytes ? sort_bytes : kept_bytes) + 16;
+}
+
+struct NmsWorkspace {
+  float* cand_key;
+  uint8_t* cand_cls;
+  int32_t* order;
+  int32_t* keep;
+};
+
+static size_t nms_ws_layout(int N, int P, void* ws, NmsWorkspace* out) {
+  const size_t np = static_cast<size_t>(N) * P;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~static_cast<size_t>(255); return o; };
+  const size_t o_key = take(np * 4), o_ord = take(np * 4), o_keep = take(np * 4), o_cls = take(np);
+  if (out && ws) {
+    unsigned char* b = static_cast<unsigned char*>(ws);
+    out->cand_key = reinterpret_cast<float*>(b + o_key);
+    out->order = reinterpret_cast<int32_t*>(b + o_ord);
+    out->keep = reinterpret_cast<int32_t*>(b + o_keep);
+    out->cand_cls = b + o_cls;
+  }
+  return off;
+}
+
+static int run_nms(float* outputs, const float* priors, int N, int P, int C, float iou_thr, float score_thr, int top_k,
+                   int per_class, int32_t* order, int32_t* order_cnt, int32_t* keep, int32_t* keep_cnt, void* ws,
+                   size_t ws_bytes, cudaStream_t st, bool fused, const char* fn) {
+  if (!outputs || N <= 0 || P <= 0 || C <= 0 || (fused && !priors)) { set_error("%s: NULL pointer or non-positive dimension", fn); return SSDH_E_ARG; }
+  if (C > kMaxClasses || P > kMaxRounds * kNmsThreads) { set_error("%s: limits are C <= %d, P <= %d", fn, kMaxClasses, kMaxRounds * kNmsThreads); return SSDH_E_LIMIT; }
+  const size_t smem = nms_smem_bytes(P);
+  if (smem > 227 * 1024) { set_error("%s: P=%d needs %zu bytes of shared memory", fn, P, smem); return SSDH_E_LIMIT; }
+  if (!ws || ws_bytes < nms_ws_layout(N, P, nullptr, nullptr)) { set_error("%s: workspace too small", fn); return SSDH_E_WORKSPACE; }
+  if (!aligned16(ws) || (fused && !aligned16(priors))) { set_error("%s: ws/priors must be 16-byte aligned", fn); return SSDH_E_ALIGN; }
+  NmsWorkspace w;
+  nms_ws_layout(N, P, ws, &w);
+  const size_t total_rows = static_cast<size_t>(N) * P;
+  const int row = 4 + C;
+  if (fused) {
+    const unsigned blocks = static_cast<unsigned>((total_rows + kTileRows - 1) / kTileRows);
+    const size_t tile_bytes = static_cast<size_t>(kTileRows) * row * sizeof(float);
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(decode_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
+    const int vec_ok = aligned16(outputs) && ((static_cast<size_t>(kTileRows) * row) % 4 == 0);
+    decode_score_kernel<<<blocks, kTileRows, tile_bytes, st>>>(outputs, reinterpret_cast<const float4*>(priors), P, C, total_rows,
+                                                              w.cand_key, w.cand_cls, vec_ok);
+  } else {
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((total_rows + 7) / 8, 148 * 16));
+    candidate_kernel<<<blocks, 256, 0, st>>>(outputs, C, total_rows, w.cand_key, w.cand_cls);
+  }
+  if (int e = cuda_status(fn)) return e;
+  static bool cfg2 = false;
+  if (!cfg2) {
+    cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e)); return static_cast<int>(e); }
+    cfg2 = true;
+  }
+  NmsParams p;
+  p.outputs = outputs; p.P = P; p.C = C;
+  p.cand_key = w.cand_key; p.cand_cls = w.cand_cls;
+  p.band = make_band(iou_thr);
+  p.score_thr = score_thr; p.top_k = top_k; p.per_class = per_class; p.scatter = fused ? 1 : 0;
+  p.order = order ? order : w.order; p.order_cnt = order_cnt;
+  p.keep = keep ? keep : w.keep; p.keep_cnt = keep_cnt;
+  nms_kernel<<<N, kNmsThreads, smem, st>>>(p);
+  return cuda_status(fn);
+}
+
+}  // namespace ssdh
+
+using namespace ssdh;
+
+extern "C" int ssdh_decode(const float* pr, int pr_row_stride, const float* priors, int N, int P, float* out, ssdh_stream_t stream) {
+  if (!pr || !priors || !out || N <= 0 || P <= 0 || pr_row_stride < 4) { set_error("ssdh_decode: bad argument"); return SSDH_E_ARG; }
+  if (!aligned16(priors) || !aligned16(out)) { set_error("ssdh_decode: priors/out must be 16-byte aligned"); return SSDH_E_ALIGN; }
+  const size_t rows = static_cast<size_t>(N) * P;
+  decode_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pr, pr_row_stride, reinterpret_cast<const float4*>(priors), P, reinterpret_cast<float4*>(out), rows);
+  return cuda_status("ssdh_decode");
+}
+
+extern "C" int ssdh_score(const float* pr, int pr_row_stride, int N, int P, int C, float* out, ssdh_stream_t stream) {
+  if (!pr || !out || N <= 0 || P <= 0 || C <= 0 || pr_row_stride < 4 + C) { set_error("ssdh_score: bad argument"); return SSDH_E_ARG; }
+  const size_t rows = static_cast<size_t>(N) * P;
+  score_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(pr, pr_row_stride, C, out, rows);
+  return cuda_status("ssdh_score");
+}
+
+extern "C" int ssdh_iou(const float* t, int t_row_stride, int T, const float* s, int s_row_stride, int S, int N, float* out,
+                        ssdh_stream_t stream) {
+  if (!t || !s || !out || N <= 0 || T <= 0 || S <= 0) { set_error("ssdh_iou: bad argument"); return SSDH_E_ARG; }
+  const size_t total = static_cast<size_t>(N) * T * S;
+  iou_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(t, t_row_stride, T, s, s_row_stride, S, out, total);
+  return cuda_status("ssdh_iou");
+}
+
+extern "C" size_t ssdh_nms_workspace_bytes(int N, int P, int C) {
+  (void)C;
+  if (N <= 0 || P <= 0) return 0;
+  return nms_ws_layout(N, P, nullptr, nullptr);
+}
+
+extern "C" int ssdh_nms(float* outputs, int N, int P, int C, float iou_thr, float score_thr, int top_k, int per_class,
+                        int32_t* order, int32_t* order_cnt, int32_t* keep, int32_t* keep_cnt, void* ws, size_t ws_bytes,
+                        ssdh_stream_t stream) {
+  return run_nms(outputs, nullptr, N, P, C, iou_thr, score_thr, top_k, per_class, order, order_cnt, keep, keep_cnt, ws, ws_bytes,
+                 static_cast<cudaStream_t>(stream), false, "ssdh_nms");
+}
+
+extern "C" int ssdh_postprocess(float* outputs, const float* priors, int N, int P, int C, float iou_thr, float score_thr,
+                                int top_k, int per_class, int32_t* order, int32_t* order_cnt, int32_t* keep, int32_t* keep_cnt,
+                                void* ws, size_t ws_bytes, ssdh_stream_t stream) {
+  return run_nms(outputs, priors, N, P, C, iou_thr, score_thr, top_k, per_class, order, order_cnt, keep, keep_cnt, ws, ws_bytes,
+                 static_cast<cudaStream_t>(stream), true, "ssdh_postprocess");
+}

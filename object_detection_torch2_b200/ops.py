@@ -1,0 +1,349 @@
+"""Tensor-level wrappers over the C ABI: argument checks, caller-owned workspaces, current-stream launches.
+
+Every function requires CUDA fp32 tensors and raises otherwise -- the product has no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, NamedTuple, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ImageStats, check
+
+NUM_PRIORS = 8732
+_ws_cache: Dict[Tuple, torch.Tensor] = {}
+_ws_retired = []      # outgrown buffers stay alive: a captured CUDA graph may still point at them
+
+
+def _need_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise RuntimeError("ssdhead kernels run on CUDA tensors only (no CPU fallback); got "
+                               f"{'a non-tensor' if not isinstance(t, torch.Tensor) else t.device}")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(kind: str, nbytes: int, device: torch.device, zero: bool = False) -> torch.Tensor:
+    """Scratch buffers are cached per (kind, device, stream) and grown on demand; the library itself never allocates."""
+    key = (kind, device.index, _stream())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)
+        buf = (torch.zeros if zero else torch.empty)(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def device_info() -> dict:
+    lib = _lib.load()
+    vals = [ctypes.c_int(0) for _ in range(4)]
+    check(lib.ssdh_device_info(*[ctypes.byref(v) for v in vals]), "ssdh_device_info")
+    return dict(sm_count=vals[0].value, max_smem_optin=vals[1].value, loss_cluster_size=vals[2].value,
+                loss_max_active_clusters=vals[3].value)
+
+
+# ------------------------------------------------------------------------------------------------ P1
+def default_boxes(device="cuda") -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(NUM_PRIORS, 4, dtype=torch.float32, device=device)
+    _need_cuda(out)
+    with torch.cuda.device(out.device):
+        check(lib.ssdh_default_boxes(out.data_ptr(), _stream()), "ssdh_default_boxes")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ L1-L6 probes
+class MatchResult(NamedTuple):
+    bits: Optional[torch.Tensor]
+    mask: Optional[torch.Tensor]
+    best_gt: Optional[torch.Tensor]
+    best_iou: Optional[torch.Tensor]
+    best_prior: Optional[torch.Tensor]
+    best_prior_iou: Optional[torch.Tensor]
+
+
+def match(gt: torch.Tensor, priors: torch.Tensor, threshold: float = 0.25, want_bits: bool = False, want_mask: bool = True,
+          want_best_gt: bool = False, want_best_prior: bool = False) -> MatchResult:
+    lib = _lib.load()
+    _need_cuda(gt, priors)
+    gt, priors = _f32c(gt), _f32c(priors)
+    N, G, stride = gt.shape
+    P = priors.shape[0]
+    dev = gt.device
+    bits = torch.empty(N, P, dtype=torch.int64, device=dev) if want_bits else None
+    mask = torch.empty(N, P, G, dtype=torch.bool, device=dev) if want_mask else None
+    bg = torch.empty(N, P, dtype=torch.int32, device=dev) if want_best_gt else None
+    bi = torch.empty(N, P, dtype=torch.float32, device=dev) if want_best_gt else None
+    bp = torch.empty(N, G, dtype=torch.int32, device=dev) if want_best_prior else None
+    bpi = torch.empty(N, G, dtype=torch.float32, device=dev) if want_best_prior else None
+    if N > 0 and P > 0:
+        with torch.cuda.device(dev):
+            check(lib.ssdh_match(gt.data_ptr(), stride, N, G, priors.data_ptr(), P, float(threshold), _ptr(bits), _ptr(mask),
+                                 _ptr(bg), _ptr(bi), _ptr(bp), _ptr(bpi), _stream()), "ssdh_match")
+    return MatchResult(bits, mask, bg, bi, bp, bpi)
+
+
+def encode(gt: torch.Tensor, priors: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(gt, priors)
+    gt, priors = _f32c(gt), _f32c(priors)
+    N, G, stride = gt.shape
+    P = priors.shape[0]
+    out = torch.empty(N, P, G, 4, dtype=torch.float32, device=gt.device)
+    if out.numel():
+        with torch.cuda.device(gt.device):
+            check(lib.ssdh_encode(gt.data_ptr(), stride, N, G, priors.data_ptr(), P, out.data_ptr(), _stream()), "ssdh_encode")
+    return out
+
+
+def smooth_l1(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(x)
+    x = _f32c(x)
+    out = torch.empty_like(x)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            check(lib.ssdh_smooth_l1(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ssdh_smooth_l1")
+    return out
+
+
+def softmax_cross_entropy(pr: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """pr (N, P, C) logits, gt (N, G, C) class weights (G may be 1 and N may broadcast) -> (N, P, G)."""
+    lib = _lib.load()
+    _need_cuda(pr, gt)
+    if pr.stride(-1) != 1 or pr.stride(0) != pr.shape[1] * pr.stride(1) or pr.dtype != torch.float32:
+        pr = _f32c(pr)
+    if gt.shape[0] != pr.shape[0]:
+        gt = gt.expand(pr.shape[0], -1, -1)
+    if gt.stride(-1) != 1 or gt.stride(0) != gt.shape[1] * gt.stride(1) or gt.dtype != torch.float32:
+        gt = _f32c(gt)
+    N, P, C = pr.shape
+    G = gt.shape[1]
+    out = torch.empty(N, P, G, dtype=torch.float32, device=pr.device)
+    if out.numel():
+        with torch.cuda.device(pr.device):
+            check(lib.ssdh_softmax_cross_entropy(pr.data_ptr(), pr.stride(1), gt.data_ptr(), gt.stride(1), N, P, G, C,
+                                                 out.data_ptr(), _stream()), "ssdh_softmax_cross_entropy")
+    return out
+
+
+def split_pos_neg(pos: torch.Tensor, neg: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    _need_cuda(pos, neg)
+    pos, neg = pos.long().contiguous(), neg.long().contiguous()
+    po, no = torch.empty_like(pos), torch.empty_like(neg)
+    if pos.numel():
+        with torch.cuda.device(pos.device):
+            check(lib.ssdh_split_pos_neg(pos.data_ptr(), neg.data_ptr(), po.data_ptr(), no.data_ptr(), pos.numel(), _stream()),
+                  "ssdh_split_pos_neg")
+    return po, no
+
+
+def kplus1_value(values: torch.Tensor, k: torch.Tensor) -> torch.Tensor:
+    """values (rows, len) or (len,), k (rows,) or 0-d int64 -> (k+1)-th largest per row."""
+    lib = _lib.load()
+    _need_cuda(values, k)
+    squeeze = values.dim() == 1
+    v = _f32c(values.unsqueeze(0) if squeeze else values)
+    kk = k.reshape(-1).long().contiguous()
+    out = torch.empty(v.shape[0], dtype=torch.float32, device=v.device)
+    with torch.cuda.device(v.device):
+        check(lib.ssdh_kplus1_value(v.data_ptr(), v.shape[0], v.shape[1], kk.data_ptr(), out.data_ptr(), _stream()), "ssdh_kplus1_value")
+    return out[0] if squeeze else out
+
+
+# ------------------------------------------------------------------------------------------------ L1-L7 fused
+STATS_DTYPE = np.dtype([("loss", "<f4"), ("thr_pos", "<f4"), ("thr_neg", "<f4"), ("pos_raw", "<i4"), ("k_pos", "<i4"),
+                        ("k_neg", "<i4"), ("pos_sel", "<i4"), ("neg_sel", "<i4")])
+assert STATS_DTYPE.itemsize == ctypes.sizeof(ImageStats)
+
+
+def multibox_loss_raw(outputs: torch.Tensor, targets: torch.Tensor, priors: torch.Tensor, a: float = 1.0, threshold: float = 0.25,
+                      n_global: Optional[int] = None, want_grad: bool = True, want_stats: bool = False,
+                      loss_out: Optional[torch.Tensor] = None, grad_out: Optional[torch.Tensor] = None,
+                      stats_out: Optional[torch.Tensor] = None):
+    """One launch: loss (0-d), d loss / d outputs (or None) and per-image stats (uint8 (N, 32) view of ssdh_image_stats, or None).
+
+    Inputs must already be contiguous fp32 CUDA tensors (this is the graph-capturable hot call)."""
+    lib = _lib.load()
+    _need_cuda(outputs, targets, priors)
+    N, P, row = outputs.shape
+    C = row - 4
+    G = targets.shape[1]
+    dev = outputs.device
+    if loss_out is None:
+        loss_out = torch.empty((), dtype=torch.float32, device=dev)
+    if want_grad and grad_out is None:
+        grad_out = torch.empty_like(outputs)
+    if want_stats and stats_out is None:
+        stats_out = torch.empty(N, ctypes.sizeof(ImageStats), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.ssdh_multibox_loss_workspace_bytes(N, P, C, G)
+        ws = _workspace("loss", nbytes, dev, zero=True)
+        check(lib.ssdh_multibox_loss(outputs.data_ptr(), targets.data_ptr() if G > 0 else None, priors.data_ptr(), N, P, C, G,
+                                     float(a), float(threshold), int(n_global or N), loss_out.data_ptr(),
+                                     _ptr(grad_out) if want_grad else None, _ptr(stats_out) if want_stats else None,
+                                     ws.data_ptr(), ws.numel(), _stream()), "ssdh_multibox_loss")
+    return loss_out, (grad_out if want_grad else None), (stats_out if want_stats else None)
+
+
+def stats_to_numpy(stats: torch.Tensor) -> np.ndarray:
+    return stats.cpu().numpy().view(STATS_DTYPE).reshape(-1)
+
+
+class _MultiBoxLossFn(torch.autograd.Function):
+    """SSD.loss with its analytic gradient produced by the same launch as the forward value."""
+
+    @staticmethod
+    def forward(ctx, outputs, targets, priors, a, threshold, n_global):
+        want_grad = ctx.needs_input_grad[0]
+        loss, grad, _ = multibox_loss_raw(outputs, targets, priors, a, threshold, n_global, want_grad=want_grad)
+        ctx.grad = grad
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        grad = ctx.grad
+        if grad is None:
+            return (None,) * 6
+        lib = _lib.load()
+        g = _f32c(g.reshape(1))
+        with torch.cuda.device(grad.device):
+            check(lib.ssdh_scale_inplace(grad.data_ptr(), grad.numel(), g.data_ptr(), _stream()), "ssdh_scale_inplace")
+        return grad, None, None, None, None, None
+
+
+def multibox_loss(outputs: torch.Tensor, targets: torch.Tensor, priors: torch.Tensor, a: float = 1.0, threshold: float = 0.25,
+                  n_global: Optional[int] = None) -> torch.Tensor:
+    """Differentiable (w.r.t. ``outputs``) MultiBox loss, 0-dim tensor."""
+    _need_cuda(outputs, targets, priors)
+    o = outputs if (outputs.dtype == torch.float32 and outputs.is_contiguous()) else outputs.float().contiguous()
+    return _MultiBoxLossFn.apply(o, _f32c(targets.detach()), _f32c(priors.detach()), float(a), float(threshold), n_global)
+
+
+# ------------------------------------------------------------------------------------------------ I1-I4
+def decode(pr: torch.Tensor, priors: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(pr, priors)
+    pr, priors = _f32c(pr), _f32c(priors)
+    N, P, stride = pr.shape
+    out = torch.empty(N, P, 4, dtype=torch.float32, device=pr.device)
+    if out.numel():
+        with torch.cuda.device(pr.device):
+            check(lib.ssdh_decode(pr.data_ptr(), stride, priors.data_ptr(), N, P, out.data_ptr(), _stream()), "ssdh_decode")
+    return out
+
+
+def score(pr: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(pr)
+    pr = _f32c(pr)
+    N, P, stride = pr.shape
+    C = stride - 4
+    out = torch.empty(N, P, C, dtype=torch.float32, device=pr.device)
+    if out.numel():
+        with torch.cuda.device(pr.device):
+            check(lib.ssdh_score(pr.data_ptr(), stride, N, P, C, out.data_ptr(), _stream()), "ssdh_score")
+    return out
+
+
+def iou(t: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(t, s)
+    t, s = _f32c(t), _f32c(s)
+    N, T, ts = t.shape
+    S, ss = s.shape[1], s.shape[2]
+    out = torch.empty(N, T, S, dtype=torch.float32, device=t.device)
+    if out.numel():
+        with torch.cuda.device(t.device):
+            check(lib.ssdh_iou(t.data_ptr(), ts, T, s.data_ptr(), ss, S, N, out.data_ptr(), _stream()), "ssdh_iou")
+    return out
+
+
+class NmsResult(NamedTuple):
+    outputs: torch.Tensor
+    order: Optional[torch.Tensor]
+    order_cnt: Optional[torch.Tensor]
+    keep: Optional[torch.Tensor]
+    keep_cnt: Optional[torch.Tensor]
+
+
+def _nms_call(fn_name: str, outputs: torch.Tensor, priors: Optional[torch.Tensor], iou_thresh: float, score_thresh: float,
+              top_k: Optional[int], per_class: bool, want_lists: bool) -> NmsResult:
+    lib = _lib.load()
+    _need_cuda(outputs, priors)
+    if outputs.dtype != torch.float32 or not outputs.is_contiguous():
+        raise RuntimeError(f"{fn_name} works in place and needs a contiguous fp32 tensor")
+    N, P, row = outputs.shape
+    C = row - 4
+    dev = outputs.device
+    order = order_cnt = keep = keep_cnt = None
+    if want_lists:
+        order = torch.empty(N, P, dtype=torch.int32, device=dev)
+        keep = torch.empty(N, P, dtype=torch.int32, device=dev)
+        order_cnt = torch.empty(N, dtype=torch.int32, device=dev)
+        keep_cnt = torch.empty(N, dtype=torch.int32, device=dev)
+    if N == 0 or P == 0:
+        return NmsResult(outputs, order, order_cnt, keep, keep_cnt)
+    with torch.cuda.device(dev):
+        ws = _workspace("nms", lib.ssdh_nms_workspace_bytes(N, P, C), dev)
+        tail = (float(iou_thresh), float(score_thresh), int(top_k or 0), int(bool(per_class)), _ptr(order), _ptr(order_cnt),
+                _ptr(keep), _ptr(keep_cnt), ws.data_ptr(), ws.numel(), _stream())
+        if priors is None:
+            check(lib.ssdh_nms(outputs.data_ptr(), N, P, C, *tail), "ssdh_nms")
+        else:
+            priors = _f32c(priors)
+            check(lib.ssdh_postprocess(outputs.data_ptr(), priors.data_ptr(), N, P, C, *tail), "ssdh_postprocess")
+    return NmsResult(outputs, order, order_cnt, keep, keep_cnt)
+
+
+def nms_(outputs: torch.Tensor, iou_thresh: float = 0.5, score_thresh: float = 0.0, top_k: Optional[int] = None,
+         per_class: bool = False, want_lists: bool = False) -> NmsResult:
+    return _nms_call("nms_", outputs, None, iou_thresh, score_thresh, top_k, per_class, want_lists)
+
+
+def postprocess_(outputs: torch.Tensor, priors: torch.Tensor, iou_thresh: float = 0.5, score_thresh: float = 0.0,
+                 top_k: Optional[int] = None, per_class: bool = False, want_lists: bool = False) -> NmsResult:
+    return _nms_call("postprocess_", outputs, priors, iou_thresh, score_thresh, top_k, per_class, want_lists)
+
+
+# ------------------------------------------------------------------------------------------------ E1-E2
+def eval_accumulate(outputs: torch.Tensor, gts: torch.Tensor, tallies: Optional[torch.Tensor] = None, iou_thresh: float = 0.5,
+                    want_flags: bool = False):
+    """Adds this batch's {TP, detections, ground truths} per class into ``tallies`` (int64 (C-1, 3))."""
+    lib = _lib.load()
+    _need_cuda(outputs, gts, tallies)
+    outputs, gts = _f32c(outputs), _f32c(gts)
+    N, P, row = outputs.shape
+    C = row - 4
+    G = gts.shape[1]
+    dev = outputs.device
+    if tallies is None:
+        tallies = torch.zeros(C - 1, 3, dtype=torch.int64, device=dev)
+    flags = torch.empty(N, P, dtype=torch.uint8, device=dev) if want_flags else None
+    if N > 0:
+        with torch.cuda.device(dev):
+            ws = _workspace("eval", lib.ssdh_eval_workspace_bytes(N, P, C, G), dev, zero=True)
+            check(lib.ssdh_eval_accumulate(outputs.data_ptr(), gts.data_ptr() if G > 0 else None, N, P, C, G, float(iou_thresh),
+                                           tallies.data_ptr(), _ptr(flags), ws.data_ptr(), ws.numel(), _stream()),
+                  "ssdh_eval_accumulate")
+    return tallies, flags

@@ -1,0 +1,51 @@
+"""Drop-in post-processing functions with the names, argument order, defaults and aliasing of the reference
+``src/utils.py`` (``calc_coordicate`` keeps the reference's spelling), running on libssdhead.so kernels."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+def calc_coordicate(pr: torch.Tensor, df: torch.Tensor) -> torch.Tensor:
+    """Offsets -> centre-form boxes, new (N, P, 4) tensor.  Reference src/utils.py:19-40."""
+    return ops.decode(pr, df)
+
+
+def calc_score(pr: torch.Tensor) -> torch.Tensor:
+    """Softmax kept at each row's arg-max class only, new (N, P, C-4) tensor.  Reference src/utils.py:43-55."""
+    return ops.score(pr)
+
+
+def calc_iou(t: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """Pairwise IoU (N, T, S) of centre-form boxes.  Reference src/utils.py:58-77."""
+    return ops.iou(t, s)
+
+
+def non_maximum_suppression(outputs: torch.Tensor, iou_thresh: float = 0.5, score_thresh: float = 0.0,
+                            top_k: Optional[int] = None, per_class: bool = False) -> torch.Tensor:
+    """Greedy class-agnostic NMS; zeroes ``outputs[:, :, 4:]`` of suppressed rows IN PLACE and returns the same
+    tensor (reference src/utils.py:80-116).  ``score_thresh`` / ``top_k`` / ``per_class`` are opt-in extensions whose
+    defaults are the reference behaviour."""
+    if outputs.dtype == torch.float32 and outputs.is_contiguous():
+        ops.nms_(outputs, iou_thresh, score_thresh, top_k, per_class)
+        return outputs
+    work = outputs.float().contiguous()          # keep the aliasing contract for odd layouts: copy back in place
+    ops.nms_(work, iou_thresh, score_thresh, top_k, per_class)
+    outputs.copy_(work)
+    return outputs
+
+
+def postprocess(outputs: torch.Tensor, df: torch.Tensor, iou_thresh: float = 0.5, score_thresh: float = 0.0,
+                top_k: Optional[int] = None, per_class: bool = False) -> torch.Tensor:
+    """The three calls of reference src/evaluate.py:129-131 / src/inference.py:67-69 as one in-place pass:
+    raw head output in, decoded boxes + NMS-masked scores out (one read and one write of the tensor)."""
+    if outputs.dtype == torch.float32 and outputs.is_contiguous():
+        ops.postprocess_(outputs, df, iou_thresh, score_thresh, top_k, per_class)
+        return outputs
+    work = outputs.float().contiguous()
+    ops.postprocess_(work, df, iou_thresh, score_thresh, top_k, per_class)
+    outputs.copy_(work)
+    return outputs

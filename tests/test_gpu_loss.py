@@ -1,0 +1,277 @@
+"""GPU parity: default boxes, matching, the loss probes and the fused MultiBox loss against the oracle and the
+reference-generated fixtures.  Everything goes through the C ABI (ctypes) of libssdhead.so.
+
+Tolerances (north_star): match masks / counts bit-exact; loss, thresholds, gradients and encoded offsets within
+1e-5 relative in fp32.  The hard-negative SELECTION is a value threshold on cross-entropies that differ in the last
+ulp between torch's CPU exp/log and the device's, so rows whose CE sits within 1e-5 of the threshold may flip; those
+rows are excluded from the element-wise gradient comparison and bounded in number.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import sha, unpack_bits
+from object_detection_torch2_b200 import ops, synth
+from object_detection_torch2_b200.model import SSD
+from oracle import head
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def priors_gpu():
+    return ops.default_boxes(DEV)
+
+
+def test_default_boxes_bit_exact(golden, priors_cpu, priors_gpu):
+    got = priors_gpu.cpu()
+    assert np.array_equal(got.numpy().view(np.uint32), golden["priors"].view(np.uint32))
+    assert torch.equal(got, priors_cpu)
+
+
+def test_device_info():
+    info = ops.device_info()
+    assert info["sm_count"] >= 100 and info["loss_cluster_size"] == 8 and info["loss_max_active_clusters"] >= 1
+
+
+@pytest.mark.parametrize("case", cases.LOSS_CASES, ids=[c[0] for c in cases.LOSS_CASES])
+def test_match_golden(case, golden, priors_cpu, priors_gpu):
+    k = f"loss/{case[0]}/"
+    o, t = cases.loss_inputs(case, priors_cpu)
+    assert sha(t) == str(golden[k + "sha_targets"])
+    r = ops.match(t.to(DEV), priors_gpu, want_bits=True, want_mask=True, want_best_gt=True, want_best_prior=True)
+    want = unpack_bits(golden[k + "match_bits"], golden[k + "match_shape"])
+    assert torch.equal(r.mask.cpu(), want)
+    G = t.shape[1]
+    bits = r.bits.cpu()
+    rebuilt = torch.stack([(bits >> g) & 1 for g in range(G)], dim=2).bool()
+    assert torch.equal(rebuilt, want)
+    # arg-max extensions against the oracle's IoU table
+    iou = torch.stack([head.pair_iou_match(t[:, g, :4], priors_cpu) for g in range(G)], dim=2)      # (N, P, G)
+    bv, bg = iou.max(dim=2)
+    assert torch.equal(r.best_iou.cpu(), bv)
+    assert torch.equal(iou.gather(2, r.best_gt.cpu().long().unsqueeze(2)).squeeze(2), bv)
+    pv, _ = iou.max(dim=1)
+    assert torch.equal(r.best_prior_iou.cpu(), pv)
+    assert torch.equal(iou.gather(1, r.best_prior.cpu().long().unsqueeze(1)).squeeze(1), pv)
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_match_batch32_vs_oracle(seed, priors_cpu, priors_gpu):
+    t = synth.make_targets(32, seed)
+    got = SSD._match(None, t.to(DEV), priors_gpu)
+    assert got.dtype == torch.bool
+    assert torch.equal(got.cpu(), head.match_mask(t, priors_cpu))
+    got = SSD._match(None, t.to(DEV), priors_gpu, threshold=0.5)
+    assert torch.equal(got.cpu(), head.match_mask(t, priors_cpu, 0.5))
+
+
+def test_probe_helpers(priors_cpu, priors_gpu, golden):
+    o, t = synth.make_batch(2, 41, "D1", 7)
+    od, td = o.to(DEV), t.to(DEV)
+    # _calc_delta: divisions are IEEE (bit-exact columns 0-1), log differs by an ulp
+    got = SSD._calc_delta(None, td, priors_gpu).cpu()
+    want = torch.stack([head.encode_offsets(t[:, g, :4], priors_cpu) for g in range(t.shape[1])], dim=2)
+    assert torch.equal(got[..., :2], want[..., :2])
+    torch.testing.assert_close(got[..., 2:], want[..., 2:], rtol=RTOL, atol=1e-6)
+    # _smooth_l1
+    x = torch.randn(10000, generator=torch.Generator().manual_seed(1)) * 2
+    assert torch.equal(SSD._smooth_l1(None, x.to(DEV)).cpu(), head.smooth_l1(x))
+    # _softmax_cross_entropy, both call shapes of ssd.py:208 and :213
+    want = -(t[:, None, :, 4:] * torch.log_softmax(o[:, :, None, 4:], dim=3)).sum(dim=3)
+    torch.testing.assert_close(SSD._softmax_cross_entropy(None, od[:, :, 4:], td[:, :, 4:]).cpu(), want, rtol=RTOL, atol=1e-6)
+    void = torch.eye(21)[0].view(1, 1, 21)
+    want = -(void[:, None] * torch.log_softmax(o[:, :, None, 4:], dim=3)).sum(dim=3)
+    torch.testing.assert_close(SSD._softmax_cross_entropy(None, od[:, :, 4:], void.to(DEV)).cpu(), want, rtol=RTOL, atol=1e-6)
+    # _split_pos_neg
+    pos = torch.tensor([0, 10, 2183, 2184, 5000, 8732])
+    kp, kn = SSD._split_pos_neg(None, pos.to(DEV), (8732 - pos).to(DEV))
+    wp, wn = head.split_pos_neg(pos, 8732)
+    assert torch.equal(kp.cpu(), wp) and torch.equal(kn.cpu(), wn)
+    # _k_plus_1_th_value: exact order statistic, incl. ties, k = 0 and negative values
+    g = torch.Generator().manual_seed(3)
+    v = torch.randn(8732, generator=g)
+    v[100:200] = v[50]
+    for k in (0, 1, 77, 4000, 8731):
+        got = SSD._k_plus_1_th_value(None, v.to(DEV), torch.tensor(k, device=DEV))
+        assert float(got) == float(head.kplus1_threshold(v, k))
+    rows = torch.rand(5, 1000, generator=g)
+    ks = torch.tensor([0, 5, 500, 998, 999])
+    got = ops.kplus1_value(rows.to(DEV), ks.to(DEV)).cpu()
+    assert torch.equal(got, torch.stack([head.kplus1_threshold(rows[i], int(ks[i])) for i in range(5)]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_and_compare(o, t, priors_cpu, priors_gpu, a=1.0, thr=0.25, max_flips=4, check_ambiguous=True):
+    """Fused kernel vs oracle on the same inputs; returns (gpu stats, oracle result)."""
+    ref = head.multibox_loss(o, t, priors_cpu, a=a, threshold=thr, want_grad=True)
+    loss, grad, stats = ops.multibox_loss_raw(o.to(DEV).contiguous(), t.to(DEV).contiguous(), priors_gpu, a=a, threshold=thr,
+                                              want_grad=True, want_stats=True)
+    st = ops.stats_to_numpy(stats)
+    assert np.array_equal(st["pos_raw"], ref["pos_raw"].numpy())
+    assert np.array_equal(st["k_pos"], ref["k_pos"].numpy())
+    assert np.array_equal(st["k_neg"], ref["k_neg"].numpy())
+    np.testing.assert_allclose(st["thr_pos"], ref["thr_pos"].numpy(), rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(st["thr_neg"], ref["thr_neg"].numpy(), rtol=RTOL, atol=1e-7)
+    assert np.abs(st["pos_sel"] - ref["pos_sel"].numpy()).max() <= max_flips
+    assert np.abs(st["neg_sel"] - ref["neg_sel"].numpy()).max() <= max_flips
+    np.testing.assert_allclose(st["loss"], ref["loss_per_image"].numpy(), rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(float(loss), float(ref["loss"]), rtol=RTOL, atol=1e-7)
+    # gradient: skip rows whose CE is within tolerance of its threshold (selection may legitimately flip)
+    near_p = (ref["ce_pos"] - ref["thr_pos"][:, None]).abs() <= 1e-5 * ref["thr_pos"][:, None].clamp(min=1.0)
+    near_n = (ref["ce_neg"] - ref["thr_neg"][:, None]).abs() <= 1e-5 * ref["thr_neg"][:, None].clamp(min=1.0)
+    member_p = ref["match"].any(dim=2)
+    ambiguous = (near_p & member_p) | (near_n & ~member_p)
+    if check_ambiguous:
+        assert int(ambiguous.sum()) <= 8 * o.shape[0] + 16
+    g = grad.cpu()
+    want = ref["grad"]
+    ok = ~ambiguous
+    scale = want.abs().max().clamp(min=1e-12)
+    err = ((g - want).abs() * ok[:, :, None]).max()
+    assert float(err) <= 1e-5 * float(scale) + 1e-10, f"grad error {float(err)} vs scale {float(scale)}"
+    rel_rows = ok[:, :, None] & (want.abs() > 1e-3 * scale)
+    assert float(((g - want).abs() / want.abs().clamp(min=1e-30))[rel_rows].max()) <= 5e-5
+    # rows that are selected by neither side carry exactly zero gradient
+    unselected = ~(ref["pos_valid"] | ref["neg_valid"]) & ok
+    assert float(g[unselected].abs().max() if unselected.any() else 0.0) == 0.0
+    return st, ref
+
+
+@pytest.mark.parametrize("case", cases.LOSS_CASES, ids=[c[0] for c in cases.LOSS_CASES])
+def test_loss_golden(case, golden, priors_cpu, priors_gpu):
+    k = f"loss/{case[0]}/"
+    o, t = cases.loss_inputs(case, priors_cpu)
+    assert sha(o) == str(golden[k + "sha_outputs"]) and sha(t) == str(golden[k + "sha_targets"]), "input generator drifted"
+    a = case[5]
+    st, ref = run_and_compare(o, t, priors_cpu, priors_gpu, a=a)
+    # against the reference's own numbers
+    x = o.to(DEV).requires_grad_(True)
+    net = SSD.__new__(SSD)
+    loss = SSD.loss(net, outputs=x, targets=t.to(DEV), default_bboxes=priors_gpu, a=a)
+    assert loss.dim() == 0
+    np.testing.assert_allclose(float(loss), float(golden[k + "loss"]), rtol=RTOL)
+    with torch.autograd.set_detect_anomaly(True):        # the reference trains under anomaly detection (train.py:102)
+        loss.backward()
+    g = x.grad.cpu()
+    np.testing.assert_allclose(g.abs().sum(dim=(1, 2)).double().numpy(), golden[k + "grad_abs_sum"], rtol=1e-4)
+    sample = g.reshape(-1)[::cases.GRAD_STRIDE].numpy()
+    want = golden[k + "grad_sample"]
+    bad = np.abs(sample - want) > 1e-5 * np.abs(want).max() + 1e-10
+    assert bad.sum() <= 2, f"{bad.sum()} sampled gradient entries differ"
+    rows = unpack_bits(golden[k + "grad_row_nonzero"], g.shape[:2])
+    flips = int(((g.abs().sum(dim=2) > 0) != rows).sum())
+    assert flips <= 4 * o.shape[0], f"{flips} rows changed selection"
+    with torch.no_grad():                                # validation pass (train.py:128-139)
+        val = SSD.loss(net, outputs=o.to(DEV), targets=t.to(DEV), default_bboxes=priors_gpu, a=a)
+    np.testing.assert_allclose(float(val), float(golden[k + "loss_nograd"]), rtol=RTOL)
+
+
+@pytest.mark.parametrize("seed,dist", [(51, "D1"), (52, "D2")])
+def test_loss_batch32_vs_oracle(seed, dist, priors_cpu, priors_gpu):
+    o, t = synth.make_batch(32, seed, dist)
+    run_and_compare(o, t, priors_cpu, priors_gpu)
+
+
+def test_loss_edge_cases(priors_cpu, priors_gpu):
+    # every ground-truth row is padding -> loss 0, gradient 0 (ssd.py:226)
+    o = synth.make_outputs(2, 61)
+    t = torch.zeros(2, 3, 25)
+    loss, grad, stats = ops.multibox_loss_raw(o.to(DEV), t.to(DEV), priors_gpu, want_stats=True)
+    assert float(loss) == 0.0 and float(grad.abs().max()) == 0.0
+    st = ops.stats_to_numpy(stats)
+    assert st["pos_raw"].tolist() == [0, 0] and st["neg_sel"].tolist() == [0, 0]
+    # G = 0 (no ground-truth rows at all)
+    loss, grad, _ = ops.multibox_loss_raw(o.to(DEV), torch.zeros(2, 0, 25, device=DEV), priors_gpu)
+    assert float(loss) == 0.0 and float(grad.abs().max()) == 0.0
+    # all-equal logits: every negative ties at the threshold, strict '>' selects none (ssd.py:223)
+    o = torch.zeros(1, 8732, 25)
+    t = synth.make_targets(1, 62, 4)
+    st, ref = run_and_compare(o, t, priors_cpu, priors_gpu, check_ambiguous=False)
+    assert int(st["neg_sel"][0]) == 0 and int(ref["neg_sel"][0]) == 0
+    # crowded image: 3 * pos > neg, only the neg // 3 hardest positives keep their terms (ssd.py:310-311)
+    t = synth.make_targets(2, 63, 20, min_boxes=20)
+    o = synth.make_outputs(2, 63)
+    st, ref = run_and_compare(o, t, priors_cpu, priors_gpu)
+    assert (st["pos_raw"] * 3 > 8732 - st["pos_raw"]).any()
+    # other match thresholds and loss weights
+    run_and_compare(o, t, priors_cpu, priors_gpu, a=0.5, thr=0.5)
+
+
+def test_loss_generic_shapes(priors_cpu, priors_gpu):
+    g = torch.Generator().manual_seed(7)
+    # fewer priors (bulk path, ragged last CTA) and a row count that defeats 16-byte chunks (fallback copy path)
+    for P in (600, 601, 37):
+        pri = priors_cpu[torch.randperm(8732, generator=g)[:P]].contiguous()
+        o = torch.randn(3, P, 25, generator=g)
+        t = synth.make_targets(3, 70 + P % 7, 6)
+        run_and_compare(o, t, pri, pri.to(DEV))
+    # class counts other than 21 take the runtime-C instantiation; soft labels take the generic CE path
+    P = 900
+    pri = priors_cpu[::9][:P].contiguous()
+    for C in (5, 33):
+        o = torch.randn(2, P, 4 + C, generator=g)
+        t = torch.zeros(2, 5, 4 + C)
+        base = synth.make_targets(2, 80 + C, 5)
+        t[:, :base.shape[1], :4] = base[:, :, :4]
+        t[:, :, 4:] = torch.rand(2, 5, C, generator=g) * (t[:, :, 2:3] > 0)
+        run_and_compare(o, t, pri, pri.to(DEV))
+
+
+def test_loss_autograd_contract(priors_gpu):
+    o, t = synth.make_batch(2, 91, "D2", 5)
+    net = SSD.__new__(SSD)
+    x = o.to(DEV).requires_grad_(True)
+    loss = net.loss(outputs=x, targets=t.to(DEV), default_bboxes=priors_gpu)      # keyword call, train.py:119-120
+    (loss * 3.0).backward()
+    y = o.to(DEV).requires_grad_(True)
+    net.loss(outputs=y, targets=t.to(DEV), default_bboxes=priors_gpu).backward()
+    torch.testing.assert_close(x.grad, 3.0 * y.grad, rtol=1e-6, atol=0)
+    # non-contiguous input: gradient flows back through the copy
+    z = o.to(DEV).transpose(0, 1).contiguous().transpose(0, 1).requires_grad_(True)
+    net.loss(outputs=z, targets=t.to(DEV), default_bboxes=priors_gpu).backward()
+    torch.testing.assert_close(z.grad, y.grad, rtol=0, atol=0)
+    with pytest.raises(RuntimeError):
+        net.loss(outputs=o, targets=t, default_bboxes=priors_gpu.cpu())              # CPU tensors: no fallback
+
+
+def test_loss_deterministic_and_graph_capturable(priors_gpu):
+    o, t = synth.make_batch(8, 93, "D1")
+    od, td = o.to(DEV), t.to(DEV)
+    l1, g1, _ = ops.multibox_loss_raw(od, td, priors_gpu)
+    l2, g2, _ = ops.multibox_loss_raw(od, td, priors_gpu)
+    assert torch.equal(l1, l2) and torch.equal(g1, g2)
+    loss = torch.empty((), device=DEV)
+    grad = torch.empty_like(od)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ops.multibox_loss_raw(od, td, priors_gpu, loss_out=loss, grad_out=grad)      # warm up on the capture stream
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            ops.multibox_loss_raw(od, td, priors_gpu, loss_out=loss, grad_out=grad)
+    torch.cuda.current_stream().wait_stream(s)
+    loss.zero_()
+    grad.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(loss, l1) and torch.equal(grad, g1)
+
+
+def test_sharded_loss_equals_whole_batch(priors_gpu):
+    # images are independent: two shards called with n_global = 8 sum to the whole-batch mean
+    from object_detection_torch2_b200 import parallel
+    o, t = synth.make_batch(8, 95, "D1")
+    od, td = o.to(DEV), t.to(DEV)
+    whole, gw, _ = ops.multibox_loss_raw(od, td, priors_gpu)
+    parts, grads = [], []
+    for r in range(2):
+        so, stt = parallel.shard_batch(od, td, 2, r)
+        l, g, _ = ops.multibox_loss_raw(so.contiguous(), stt.contiguous(), priors_gpu, n_global=8)
+        parts.append(l)
+        grads.append(g)
+    torch.testing.assert_close(parts[0] + parts[1], whole, rtol=1e-6, atol=0)
+    assert torch.equal(torch.cat(grads), gw)

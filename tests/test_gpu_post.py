@@ -1,0 +1,191 @@
+"""GPU parity: decode, score, IoU, NMS (stand-alone and fused) and the evaluation tallies, through the C ABI.
+
+Index results (sort order, keep lists, TP flags, tallies) are compared bit-exactly ON IDENTICAL INPUTS: the NMS and
+evaluation kernels are fed the oracle's decoded + scored tensor, as north_star words it.  Decoded boxes and scores
+themselves are held to 1e-5 relative (exp differs in the last ulp between torch's CPU kernels and the device).
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import sha, unpack_bits
+from object_detection_torch2_b200 import evaluate, ops, synth, utils
+from oracle import head
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def priors_gpu():
+    return ops.default_boxes(DEV)
+
+
+def scored_cpu(o, priors_cpu):
+    x = o.clone()
+    x[:, :, :4] = head.decode_boxes(x, priors_cpu)
+    x[:, :, 4:] = head.class_scores(x)
+    return x
+
+
+def lists(res, n):
+    order = res.order[n, : int(res.order_cnt[n])].cpu().long()
+    keep = res.keep[n, : int(res.keep_cnt[n])].cpu().long()
+    return order, keep
+
+
+@pytest.mark.parametrize("case", cases.POST_CASES, ids=[c[0] for c in cases.POST_CASES])
+def test_post_golden(case, golden, priors_cpu, priors_gpu):
+    k = f"post/{case[0]}/"
+    o, t = cases.post_inputs(case, priors_cpu)
+    assert sha(o) == str(golden[k + "sha_outputs"]) and sha(t) == str(golden[k + "sha_targets"]), "input generator drifted"
+    od = o.to(DEV)
+    # I1 / I2 with the reference's call pattern (evaluate.py:129-130)
+    box = utils.calc_coordicate(pr=od, df=priors_gpu)
+    np.testing.assert_allclose(box.cpu().reshape(-1)[::7].numpy(), golden[k + "box_sample"], rtol=1e-5, atol=1e-7)
+    assert torch.equal(box[..., :2].cpu(), head.decode_boxes(o, priors_cpu)[..., :2])         # mul + add: bit-exact
+    od[:, :, :4] = box
+    sc = utils.calc_score(pr=od)
+    assert sc.shape == (o.shape[0], 8732, 21)
+    assert np.array_equal(sc.argmax(dim=2).cpu().numpy().astype(np.uint8), golden[k + "score_argmax"])
+    np.testing.assert_allclose(sc.max(dim=2).values.cpu().numpy(), golden[k + "score_max"], rtol=1e-5)
+    assert int((sc > 0).sum(dim=2).max()) == 1
+    # I3 + I4 + E on the oracle's scored tensor (identical inputs -> bit-exact indices)
+    x = scored_cpu(o, priors_cpu)
+    xd = x.to(DEV)
+    assert torch.equal(utils.calc_iou(xd[:, :64], t.to(DEV)).cpu(), torch.from_numpy(golden[k + "iou_gt_64"]))
+    y = utils.non_maximum_suppression(outputs=xd, iou_thresh=case[4])
+    assert y is xd
+    kept_rows = (y[:, :, 4:].sum(dim=2) > 0).cpu()
+    assert torch.equal(kept_rows, unpack_bits(golden[k + "kept_rows"], kept_rows.shape))
+    assert sha(y.cpu()) == str(golden[k + "sha_after_nms"])
+    tallies, flags = evaluate.accumulate(y, t.to(DEV), want_flags=True)
+    assert np.array_equal(tallies.cpu().numpy(), golden[k + "tallies"])
+    # TP flags in the reference's order: class-major, then image, then descending score
+    yc, fl = y.cpu(), flags.cpu()
+    got = []
+    for c in range(20):
+        for n in range(o.shape[0]):
+            det = head.class_order(yc[n], c)
+            got.append(fl[n, det].numpy())
+    got = np.concatenate(got) if got else np.zeros(0, np.uint8)
+    assert np.array_equal(got, golden[k + "tp_flags"])
+    ap = evaluate.average_precision_from_tallies(tallies).cpu().numpy()
+    want = golden[k + "ap"]
+    has = ~np.isnan(want)
+    np.testing.assert_allclose(ap[has], want[has], rtol=1e-6)
+
+
+@pytest.mark.parametrize("seed,dist,n", [(101, "D2", 4), (102, "D1", 2)])
+def test_nms_lists_vs_oracle(seed, dist, n, priors_cpu):
+    o, t = synth.make_batch(n, seed, dist)
+    o = synth.plant_detections(o, t, priors_cpu, seed)
+    x = scored_cpu(o, priors_cpu)
+    for kw in (dict(iou_thresh=0.5), dict(iou_thresh=0.45, score_thresh=0.3), dict(iou_thresh=0.45, top_k=200),
+               dict(iou_thresh=0.3, per_class=True), dict(iou_thresh=0.45, score_thresh=0.01, top_k=200, per_class=True)):
+        xd = x.to(DEV)
+        res = ops.nms_(xd, want_lists=True, **kw)
+        want = x.clone()
+        want, _ = head.nms_inplace(want, **kw)
+        for i in range(n):
+            order, keep = lists(res, i)
+            o_want, k_want = head.greedy_nms(x[i], **kw)
+            assert torch.equal(order, o_want), kw
+            assert torch.equal(keep, k_want), kw
+        assert torch.equal(xd.cpu(), want), kw
+
+
+def test_nms_edge_cases():
+    rows = torch.zeros(1, 64, 25)
+    xd = rows.to(DEV)
+    res = ops.nms_(xd, want_lists=True)                                  # no candidates at all
+    assert int(res.order_cnt[0]) == 0 and int(res.keep_cnt[0]) == 0 and float(xd.abs().max()) == 0.0
+    rows[0, :, :4] = torch.tensor([.5, .5, .2, .2])
+    rows[0, :, 6] = 0.9                                                  # 64 identical boxes, identical scores
+    rows[0, 10, 4] = 1.0
+    rows[0, 10, 6] = 0.0                                                 # void row among them
+    xd = rows.to(DEV)
+    res = ops.nms_(xd, want_lists=True)
+    order, keep = lists(res, 0)
+    assert order.tolist() == [i for i in range(64) if i != 10]            # stable: ties keep row order
+    assert keep.tolist() == [0]
+    assert float(xd[0, 10, 4]) == 0.0                                    # void score of a non-candidate is masked too
+    single = torch.zeros(1, 5, 25)
+    single[0, 3, :4] = torch.tensor([.3, .3, .1, .1])
+    single[0, 3, 9] = 0.7
+    sd = single.to(DEV)
+    res = ops.nms_(sd, want_lists=True)
+    assert lists(res, 0)[1].tolist() == [3] and torch.equal(sd.cpu(), single)
+    with pytest.raises(RuntimeError):
+        ops.nms_(torch.zeros(1, 4, 25))                                  # CPU tensor: no fallback
+
+
+def test_fused_postprocess_equals_staged(priors_cpu, priors_gpu):
+    o, t = synth.make_batch(6, 111, "D2")
+    o = synth.plant_detections(o, t, priors_cpu, 111)
+    staged = o.to(DEV)
+    staged[:, :, :4] = utils.calc_coordicate(pr=staged, df=priors_gpu)
+    staged[:, :, 4:] = utils.calc_score(pr=staged)
+    scored = staged.clone()
+    staged = utils.non_maximum_suppression(outputs=staged, iou_thresh=0.45)
+    fused = o.to(DEV)
+    out = utils.postprocess(fused, priors_gpu, iou_thresh=0.45)
+    assert out is fused
+    assert torch.equal(fused, staged)
+    # and both equal the oracle's NMS applied to the device's own decoded + scored tensor
+    want, _ = head.nms_inplace(scored.cpu(), iou_thresh=0.45)
+    assert torch.equal(fused.cpu(), want)
+    # end to end against the pure-CPU oracle pipeline: boxes within 1e-5, same rows kept
+    pure, keeps = head.nms_inplace(scored_cpu(o, priors_cpu), iou_thresh=0.45)
+    torch.testing.assert_close(fused[:, :, :4].cpu(), pure[:, :, :4], rtol=1e-5, atol=1e-7)
+    same = ((fused[:, :, 4:].sum(dim=2) > 0).cpu() == (pure[:, :, 4:].sum(dim=2) > 0)).float().mean()
+    assert float(same) > 0.9995
+
+
+def test_nms_properties_full_size(priors_gpu):
+    # config 3 of BASELINE.json at full width: batch 256; size-independent invariants instead of the (slow) oracle
+    o = synth.make_outputs(256, 121, "D2").to(DEV)
+    res = ops.postprocess_(o, priors_gpu, iou_thresh=0.45, want_lists=True)
+    kc, oc = res.keep_cnt.cpu(), res.order_cnt.cpu()
+    assert int(oc.min()) > 0 and bool((kc <= oc).all()) and bool((kc > 0).all())
+    scores = o[:, :, 4:]
+    assert int((scores > 0).sum(dim=2).max()) == 1                                   # at most one class per row
+    assert torch.equal((scores.sum(dim=2) > 0).sum(dim=1).cpu().int(), kc)           # exactly the kept rows keep a score
+    assert float(scores[:, :, 0].abs().max()) == 0.0                                 # void column always masked
+    # kept boxes are mutually non-overlapping above the threshold (spot-check 8 images)
+    for n in range(0, 256, 32):
+        keep = res.keep[n, : int(kc[n])].long()
+        boxes = o[n, keep][None, :, :4]
+        iou = utils.calc_iou(boxes, boxes)[0]
+        iou.fill_diagonal_(0)
+        assert float(iou.max()) <= 0.45
+        key = o[n, keep, 5:].max(dim=1).values
+        assert bool((key[:-1] >= key[1:]).all())                                     # kept list is in score order
+    # idempotence: NMS of an NMS result changes nothing
+    again = o.clone()
+    ops.nms_(again, iou_thresh=0.45)
+    assert torch.equal(again, o)
+
+
+def test_eval_planted_vs_oracle(priors_cpu):
+    o, t = synth.make_batch(8, 131, "D2", 12)
+    o = synth.plant_detections(o, t, priors_cpu, 131, per_gt=4, jitter=0.3)
+    x, _ = head.nms_inplace(scored_cpu(o, priors_cpu))
+    want, _ = head.eval_batch(x, t)
+    tallies = torch.zeros(20, 3, dtype=torch.int64, device=DEV)
+    for lo in (0, 4):                                                   # two batches accumulate into one tally
+        evaluate.accumulate(x[lo:lo + 4].to(DEV), t[lo:lo + 4].to(DEV), tallies)
+    assert torch.equal(tallies.cpu(), want)
+    assert int(want[:, 0].sum()) > 20
+    # an image without ground truth and an image without detections
+    x2 = x[:2].clone()
+    t2 = t[:2].clone()
+    t2[0] = 0
+    x2[1, :, 4:] = 0
+    want2, _ = head.eval_batch(x2, t2)
+    got2, _ = evaluate.accumulate(x2.to(DEV), t2.to(DEV))
+    assert torch.equal(got2.cpu(), want2)
+    res = torch.tensor([[1., .9], [0., .8], [1., .7], [0., .6]])
+    assert float(evaluate.calc_average_precision(res.to(DEV), 4)) == pytest.approx(float(head.average_precision(res, 4)))
+    assert evaluate.get_order(x[0].to(DEV), 3).cpu().tolist() == head.class_order(x[0], 3).tolist()
