@@ -3,18 +3,21 @@
 // _split_pos_neg, _k_plus_1_th_value) plus the autograd backward of that graph (src/train.py:121).
 //
 // Decomposition (B200, sm_100a):
-//   * one thread-block CLUSTER of 8 CTAs per image; CTA r owns rows [r*R, (r+1)*R) of the image's
-//     contiguous [P, 4+C] slab (R = 1092 for P = 8732) and keeps them in shared memory for the whole
-//     kernel, so HBM sees each output row exactly once as a read and (with grad) once as a write;
-//   * the slab arrives by TMA bulk copies (cp.async.bulk + mbarrier, one chunk per row slot) while the
-//     threads compute the IoU match masks, which only need the priors and the ground truth;
+//   * one thread-block CLUSTER per image (4 CTAs x 768 threads, one CTA per SM; 8 x 384 for bigger slabs).
+//     The image's contiguous [P, 4+C] slab is cut into 32-row blocks dealt round-robin to the CTAs, so every
+//     CTA sees the same mix of prior levels (equal matching work) and keeps its rows in shared memory for
+//     the whole kernel: HBM sees each output row exactly once as a read and (with grad) once as a write;
+//   * blocks arrive by TMA bulk copies (cp.async.bulk + mbarrier, one barrier per row slot), issued right
+//     after the (tiny, latency-critical) ground-truth rows landed; the IoU matching runs under the bulk load;
 //   * one thread per row: log-sum-exp, positive / negative cross-entropy, smooth-L1 of matched pairs;
-//   * hard-negative mining = value threshold at the (k+1)-th largest CE (strict '>', ssd.py:222-223),
-//     found by an 8-bit radix select whose per-CTA histograms are combined through distributed shared
-//     memory; only ONE of the two thresholds ever needs a search (see select logic below);
+//   * hard-negative mining = value threshold at the (k+1)-th largest CE (strict '>', ssd.py:222-223):
+//     a 256-bucket histogram (1/16-octave buckets of the CE) is combined through distributed shared memory,
+//     the bucket's candidates are gathered into every CTA and the exact order statistic is finished locally;
+//     only ONE of the two thresholds ever needs a search (see the split logic below);
 //   * gradient rows are written in place over the slab and leave by TMA bulk stores;
 //   * the last image to finish reduces the per-image losses in a fixed order (deterministic).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -22,10 +25,15 @@ namespace cg = cooperative_groups;
 
 namespace ssdh {
 
-constexpr int kLossThreads = 384;
 constexpr int kSlots = 3;            // rows per thread
-constexpr int kCluster = 8;
-constexpr int kLossWarps = kLossThreads / 32;
+constexpr int kBlockRows = 32;       // rows per dealt block (one warp-row)
+constexpr int kMaxCluster = 8;
+constexpr int kMaxLossWarps = 32;
+constexpr int kListCap = 384;        // per-CTA candidates of the selected bucket
+constexpr int kGatherCap = 768;      // cluster-wide candidates finished locally
+// Two shapes of the same kernel (template parameters kT = threads per CTA, kCl = CTAs per cluster):
+//   <768, 4>: 4 CTAs x ~221 KB per image, one CTA per SM  -> every SM carries the same load (default when it fits)
+//   <384, 8>: 8 CTAs x ~110 KB per image                   -> larger images / more ground truth per image
 
 struct LossParams {
   const float* outputs;
@@ -40,9 +48,21 @@ struct LossParams {
   ssdh_image_stats* stats;
   unsigned int* ticket;   // workspace: zero before first use, left zero
   double* image_loss;     // workspace [N]
-  int rows_per_cta;
-  int bulk;               // 1: every chunk is 16-byte aligned/sized -> TMA path
+  int rows_per_cta;       // shared-memory rows reserved per CTA (multiple of kBlockRows)
+  int n_blocks;           // ceil(P / kBlockRows)
+  int bulk;               // 1: every block is 16-byte aligned/sized -> TMA path
+  unsigned long long* trace;   // debug: [grid][kTracePoints] SM clock stamps (NULL in production)
 };
+
+constexpr int kTracePoints = 64;
+__device__ __forceinline__ void trace_point(const LossParams& p, int idx) {
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    if (idx == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    else t = clock64();
+    p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + idx] = t;
+  }
+}
 
 struct GtRec {             // 48 bytes, one per ground-truth row of the image
   float x1, x2, y1, y2;    // corners                      (ssd.py:247-248)
@@ -56,14 +76,17 @@ struct GtRec {             // 48 bytes, one per ground-truth row of the image
 struct LossShared {
   uint32_t hist[2][2][128];   // [buffer][set][256 bins packed as 2 x u16]
   uint32_t tot[2][128];       // cluster-wide packed totals
-  unsigned long long mbar[kSlots];
-  unsigned long long deg_mask, deg_hit;   // gt rows with area <= 0 and their constant verdict
-  double part_loss[kCluster];             // leader only: written remotely by every CTA
-  int part_pos_sel[kCluster], part_neg_sel[kCluster];
-  double wred_loss[kLossWarps];
-  int wred_a[kLossWarps], wred_b[kLossWarps];
-  int pos_local;
-  int pos_raw, k_pos, k_neg, sel_set, need_select;
+  uint32_t list[kListCap];    // my candidates of the selected bucket (read remotely)
+  uint32_t gathered[kGatherCap];
+  unsigned long long mbar[kSlots][kMaxLossWarps];   // one per (row slot, warp): a warp's 32 rows are one dealt block
+  uint8_t gt_fast[kMaxGT], gt_slow[kMaxGT];          // ground-truth rows by matching path (see the match section)
+  int n_fast, n_slow, soft_labels;
+  double part_loss[kMaxCluster];          // leader only: written remotely by every CTA
+  int part_pos_sel[kMaxCluster], part_neg_sel[kMaxCluster];
+  double wred_loss[kMaxLossWarps];
+  int wred_a[kMaxLossWarps], wred_b[kMaxLossWarps];
+  int pos_local, list_cnt;                // read remotely
+  int pos_raw, k_pos, k_neg, sel_set, need_select, overflow, n_gathered;
   uint32_t sel_prefix, sel_rem;
 };
 
@@ -97,17 +120,79 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Ampere-style async copies (LDGSTS): 16 bytes per lane, completion tracked per thread in commit groups.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
 __device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Packed fp32 pairs (FFMA2 / FADD2 on sm_100a): one issue slot for two lanes of the class loop.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 
 __device__ __forceinline__ float smooth_l1_f(float x) {
   const float ax = fabsf(x);
   return ax < 1.0f ? 0.5f * x * x : ax - 0.5f;
+}
+__device__ __forceinline__ float clamp1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
+
+// In place: x[c] <- scale * exp(x[c] - lse), the softmax gradient term of one row of logits in shared memory.
+template <int kC>
+__device__ __forceinline__ void softmax_scaled(float* x, int C, float lse, float scale) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float nls = -(lse * kLog2e);
+  if (kC > 0) {
+    const unsigned long long l2 = pack2(kLog2e, kLog2e), m2 = pack2(nls, nls), sc2 = pack2(scale, scale);
+#pragma unroll
+    for (int c = 0; c + 1 < kC; c += 2) {
+      float a0, a1;
+      unpack2(ffma2(pack2(x[c], x[c + 1]), l2, m2), a0, a1);
+      unpack2(fmul2(pack2(ex2_approx(a0), ex2_approx(a1)), sc2), a0, a1);
+      x[c] = a0;
+      x[c + 1] = a1;
+    }
+    if (kC & 1) x[kC - 1] = scale * ex2_approx(fmaf(x[kC - 1], kLog2e, nls));
+  } else {
+    for (int c = 0; c < C; ++c) x[c] = scale * ex2_approx(fmaf(x[c], kLog2e, nls));
+  }
+}
+
+// Monotone (non-decreasing in the order key) 8-bit bucket: 16 buckets per octave over [2^-12, 2^4), everything
+// below / above clamps into the first / last bucket.  Cross-entropies of interest live well inside the window.
+__device__ __forceinline__ uint32_t bucket_of(uint32_t key) {
+  const int v = static_cast<int>(key >> 19) - (4096 + ((127 - 12) << 4));
+  return static_cast<uint32_t>(min(max(v, 0), 255));
 }
 
 // One warp: find the bin holding the (rem+1)-th largest element of a 256-bin packed histogram.
@@ -124,17 +209,19 @@ __device__ __forceinline__ int find_bin_desc(const uint32_t* packed, uint32_t& r
   const int incl = warp_incl_scan(s, lane);
   const uint32_t ballot = __ballot_sync(0xffffffffu, static_cast<uint32_t>(incl) > rem);
   const int owner = ballot ? (__ffs(ballot) - 1) : 31;
-  int bin = 0;
-  uint32_t r = 0;
-  if (lane == owner) {
-    r = rem - static_cast<uint32_t>(incl - s);
-    int i = 0;
-    for (; i < 7; ++i) {
-      if (r < c[i]) break;
-      r -= c[i];
-    }
-    bin = 255 - 8 * lane - i;
+  // inside the owner's 8 bins (descending): first i with rem' < c[0] + ... + c[i], branch-free
+  const uint32_t r0 = rem - static_cast<uint32_t>(incl - s);
+  uint32_t cum = 0, below = 0;
+  int idx = 0;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    cum += c[i];
+    const bool past = r0 >= cum;
+    idx += past ? 1 : 0;
+    below = past ? cum : below;
   }
+  int bin = 255 - 8 * lane - idx;
+  uint32_t r = r0 - below;
   bin = __shfl_sync(0xffffffffu, bin, owner);
   rem = __shfl_sync(0xffffffffu, r, owner);
   return bin;
@@ -148,8 +235,10 @@ __device__ __forceinline__ void hist_add(uint32_t* hist_set0, bool active, int s
     atomicAdd(hist_set0 + set * 128 + (bin >> 1), static_cast<uint32_t>(__popc(peers)) << (16 * (bin & 1u)));
 }
 
-template <int kC>
-__global__ void __launch_bounds__(kLossThreads, 2) multibox_loss_kernel(const LossParams p) {
+template <int kC, int kLossThreads, int kCluster>
+__global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const LossParams p) {
+  constexpr int kLossWarps = kLossThreads / 32;
+  constexpr int kSlotBlocks = kLossThreads / kBlockRows;      // dealt blocks per row slot
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = static_cast<int>(cluster.block_rank());
   const int n = blockIdx.x / kCluster;
@@ -157,8 +246,9 @@ __global__ void __launch_bounds__(kLossThreads, 2) multibox_loss_kernel(const Lo
   const int row = 4 + C;
   const int G = p.G;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row0 = rank * p.rows_per_cta;
-  const int my_rows = max(0, min(p.rows_per_cta, p.P - row0));
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  // CTA `rank` owns global blocks rank, rank + kCluster, ...; local block j <-> global block j * kCluster + rank
+  const int my_blocks = (p.n_blocks - rank + kCluster - 1) / kCluster;
   constexpr float kLog2e = 1.4426950408889634f;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -167,166 +257,275 @@ __global__ void __launch_bounds__(kLossThreads, 2) multibox_loss_kernel(const Lo
   GtRec* gts = reinterpret_cast<GtRec*>(smem_raw + slab_bytes);
   LossShared& sh = *reinterpret_cast<LossShared*>(smem_raw + slab_bytes + ((static_cast<size_t>(G) * sizeof(GtRec) + 15) & ~static_cast<size_t>(15)));
 
-  const float* src = p.outputs + (static_cast<size_t>(n) * p.P + row0) * row;
+  const float* img_in = p.outputs + static_cast<size_t>(n) * p.P * row;
 
   // ---- setup ------------------------------------------------------------------------------------
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) mbar_init(&sh.mbar[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    sh.pos_local = 0;
-    sh.deg_mask = 0ull;
-    sh.deg_hit = 0ull;
-  }
-  for (int i = tid; i < 2 * 2 * 128; i += kLossThreads) (&sh.hist[0][0][0])[i] = 0u;
-  __syncthreads();
-
-  if (p.bulk) {
-    if (tid == 0) {
-#pragma unroll
-      for (int s = 0; s < kSlots; ++s) {
-        const int rows_s = min(kLossThreads, my_rows - s * kLossThreads);
-        if (rows_s > 0) {
-          const uint32_t bytes = static_cast<uint32_t>(rows_s) * row * sizeof(float);
-          mbar_expect_tx(&sh.mbar[s], bytes);
-          bulk_load(slab + static_cast<size_t>(s) * kLossThreads * row, src + static_cast<size_t>(s) * kLossThreads * row, bytes, &sh.mbar[s]);
-        }
-      }
-    }
-  } else {
-    const int total = my_rows * row;
-    for (int i = tid; i < total; i += kLossThreads) slab[i] = src[i];
-  }
-
-  // ---- ground truth of this image -> shared -------------------------------------------------------
-  for (int g = tid; g < G; g += kLossThreads) {
-    const float* tr = p.targets + (static_cast<size_t>(n) * G + g) * row;
-    const float gcx = tr[0], gcy = tr[1], gw = tr[2], gh = tr[3];
-    const Corners c = make_corners(gcx, gcy, gw, gh);
-    GtRec r;
-    r.x1 = c.x1; r.x2 = c.x2; r.y1 = c.y1; r.y2 = c.y2;
-    r.area = c.area; r.cx = gcx; r.cy = gcy;
-    r.lw = gw > 0.0f ? logf(gw) : gw;
-    r.lh = gh > 0.0f ? logf(gh) : gh;
-    r.flags = (gw > 0.0f ? 1 : 0) | (gh > 0.0f ? 2 : 0);
-    int nz = 0, label = -1;
-    float tsum = 0.0f;
-    for (int c2 = 0; c2 < C; ++c2) {
-      const float v = tr[4 + c2];
-      tsum += v;
-      if (v != 0.0f) { ++nz; label = (v == 1.0f) ? c2 : -1 - C; }
-    }
-    r.label = (nz == 1 && label >= 0) ? label : -1;
-    r.tsum = tsum;
-    gts[g] = r;
-    if (!(c.area > 0.0f)) {
-      atomicOr(&sh.deg_mask, 1ull << g);
-      if (c.area > p.band.thr) atomicOr(&sh.deg_hit, 1ull << g);
-    }
-  }
-
-  // ---- priors of my rows ------------------------------------------------------------------------------
-  Corners d[kSlots];
+  trace_point(p, 0);
+  trace_point(p, 1);
+  float4 pri[kSlots];
   bool valid[kSlots];
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) {
     const int lr = s * kLossThreads + tid;
-    valid[s] = lr < my_rows;
-    const float4 q = p.priors[valid[s] ? row0 + lr : 0];
-    d[s] = make_corners(q.x, q.y, q.z, q.w);
+    const int grow = (((lr >> 5) * kCluster + rank) << 5) + (lr & 31);
+    valid[s] = ((lr >> 5) < my_blocks) && (grow < p.P);
+    pri[s] = __ldg(p.priors + (valid[s] ? grow : 0));
+  }
+  if (tid == 0) {
+    sh.pos_local = 0;
+    sh.list_cnt = 0;
+    sh.n_fast = 0;
+    sh.n_slow = 0;
+    sh.soft_labels = 0;
+  }
+  for (int i = tid; i < 2 * 2 * 128; i += kLossThreads) (&sh.hist[0][0][0])[i] = 0u;
+  __syncthreads();
+
+  // The (tiny) ground-truth rows are requested first so they are not queued behind the slab traffic.
+  float gt_first = 0.0f;
+  if (warp < G) gt_first = __ldg(p.targets + (static_cast<size_t>(n) * G + warp) * row + min(lane, row - 1));
+
+  // ---- ground truth of this image -> shared: one warp per row, one coalesced request each -----------------
+  for (int g = warp; g < G; g += kLossWarps) {
+    const float* tr = p.targets + (static_cast<size_t>(n) * G + g) * row;
+    float box = 0.0f, tsum = 0.0f;
+    int nz = 0, ones = 0, label = -1;
+    for (int base = 0; base < row; base += 32) {
+      const int c = base + lane;
+      const float v = (base == 0 && g == warp) ? (c < row ? gt_first : 0.0f) : (c < row ? __ldg(tr + c) : 0.0f);
+      if (base == 0) box = v;
+      const bool cls = c >= 4 && c < row;
+      const uint32_t b_nz = __ballot_sync(0xffffffffu, cls && v != 0.0f);
+      const uint32_t b_one = __ballot_sync(0xffffffffu, cls && v == 1.0f);
+      nz += __popc(b_nz);
+      ones += __popc(b_one);
+      if (b_one) label = base + __ffs(b_one) - 1 - 4;
+      tsum += warp_sum(cls ? v : 0.0f);
+    }
+    const float gcx = __shfl_sync(0xffffffffu, box, 0), gcy = __shfl_sync(0xffffffffu, box, 1);
+    const float gw = __shfl_sync(0xffffffffu, box, 2), gh = __shfl_sync(0xffffffffu, box, 3);
+    if (lane == 0) {
+      const Corners c = make_corners(gcx, gcy, gw, gh);
+      GtRec r;
+      r.x1 = c.x1; r.x2 = c.x2; r.y1 = c.y1; r.y2 = c.y2;
+      r.area = c.area; r.cx = gcx; r.cy = gcy;
+      r.lw = gw > 0.0f ? logf(gw) : gw;
+      r.lh = gh > 0.0f ? logf(gh) : gh;
+      r.flags = (gw > 0.0f ? 1 : 0) | (gh > 0.0f ? 2 : 0);
+      r.label = (nz == 1 && ones == 1) ? label : -1;
+      r.tsum = tsum;
+      gts[g] = r;
+      // fast path: a normal positive area lets the band test decide IoU > thr without dividing; everything else
+      // (padding rows, degenerate or denormal boxes, exotic thresholds) takes the exact path
+      if (p.band.usable && c.area >= 1e-30f && c.area <= 1e30f) sh.gt_fast[atomicAdd(&sh.n_fast, 1)] = static_cast<uint8_t>(g);
+      else if (c.area > 0.0f || c.area > p.band.thr || !(c.area == c.area)) sh.gt_slow[atomicAdd(&sh.n_slow, 1)] = static_cast<uint8_t>(g);
+      if (r.label < 0 && c.area > 0.0f) sh.soft_labels = 1;
+    }
   }
   __syncthreads();
 
-  // ---- matching: bit g of mask[s] = IoU(gt g, prior) > thr   (ssd.py:231-250) ---------------------------
-  unsigned long long mask[kSlots];
+  // ---- slab: every warp fetches its own dealt blocks (one per row slot) by TMA bulk copy onto its own mbarriers;
+  // issued only now, after the ground truth landed, so the small loads were never queued behind this traffic ----
+  if (p.bulk) {
+    if (lane == 0) {
 #pragma unroll
-  for (int s = 0; s < kSlots; ++s) mask[s] = 0ull;
-  {
-    const unsigned long long deg_mask = sh.deg_mask, deg_hit = sh.deg_hit;
-    const ThrBand band = p.band;
-    for (int g = 0; g < G; ++g) {
-      const unsigned long long bit = 1ull << g;
-      if (deg_mask & bit) {
-        if (deg_hit & bit) {
-#pragma unroll
-          for (int s = 0; s < kSlots; ++s) mask[s] |= bit;
-        }
-        continue;
-      }
-      const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
-      const float garea = gts[g].area;
+      for (int s = 0; s < kSlots; ++s) mbar_init(&sh.mbar[s][warp], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
       for (int s = 0; s < kSlots; ++s) {
-        const float w = fmaxf(fminf(q.y, d[s].x2) - fmaxf(q.x, d[s].x1), 0.0f);
-        const float h = fmaxf(fminf(q.w, d[s].y2) - fmaxf(q.z, d[s].y1), 0.0f);
-        const float inter = w * h;
-        const float uni = (garea + d[s].area) - inter;
-        if (quotient_gt(inter, uni, band)) mask[s] |= bit;
+        const int j = s * kSlotBlocks + warp;
+        if (j < my_blocks) {
+          const int gb = j * kCluster + rank;
+          const uint32_t bytes = static_cast<uint32_t>(min(kBlockRows, p.P - gb * kBlockRows)) * row * sizeof(float);
+          mbar_expect_tx(&sh.mbar[s][warp], bytes);
+          bulk_load(slab + static_cast<size_t>(j) * kBlockRows * row, img_in + static_cast<size_t>(gb) * kBlockRows * row, bytes, &sh.mbar[s][warp]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+      const int j = s * kSlotBlocks + warp;
+      if (j < my_blocks) {
+        const int gb = j * kCluster + rank;
+        const int nfl = min(kBlockRows, p.P - gb * kBlockRows) * row;
+        const float* src = img_in + static_cast<size_t>(gb) * kBlockRows * row;
+        float* dst = slab + static_cast<size_t>(j) * kBlockRows * row;
+        for (int i = lane; i < nfl; i += 32) dst[i] = src[i];
+      }
+    }
+    __syncwarp();
+  }
+
+  Corners d[kSlots];
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) d[s] = make_corners(pri[s].x, pri[s].y, pri[s].z, pri[s].w);
+
+  trace_point(p, 2);
+  // ---- matching: bit g of (mhi:mlo)[s] = IoU(gt g, prior) > thr   (ssd.py:231-250) ----------------------------
+  // Dense pass over the fast rows, branch-free and division-free.  e = inter - union * thr is one FMA, so its sign
+  // is exact; |e| > union * thr * 2^-20 then decides fl(inter / union) > thr with certainty either way.  The
+  // (one in millions) pairs inside that band flag the thread through `amb`, and a flagged thread redoes its pairs
+  // with the IEEE division, so the final mask is bit-identical to torch's.  The min / max / compare / logic ops
+  // issue at half rate on this SM, hence the care to keep them at 9 per pair.
+  uint32_t mlo[kSlots], mhi[kSlots];
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) { mlo[s] = 0u; mhi[s] = 0u; }
+  {
+    const ThrBand band = p.band;
+    const float nthr = -band.thr, eps = band.thr * 9.5367431640625e-07f;
+    const int n_fast = sh.n_fast, n_slow = sh.n_slow;
+    float amb = 1.0f;                              // min over pairs of |e| - margin; <= 0 means "settle exactly"
+#pragma unroll 2
+    for (int i = 0; i < n_fast; ++i) {
+      const int g = sh.gt_fast[i];
+      const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
+      const float garea = gts[g].area;
+      const uint32_t bit = 1u << (g & 31);
+      if (g < 32) {
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+          const float w = fmaxf(fminf(q.y, d[s].x2) - fmaxf(q.x, d[s].x1), 0.0f);
+          const float h = fmaxf(fminf(q.w, d[s].y2) - fmaxf(q.z, d[s].y1), 0.0f);
+          const float inter = w * h;
+          const float uni = (garea + d[s].area) - inter;
+          const float e = fmaf(uni, nthr, inter), m = uni * eps;
+          amb = fminf(amb, fabsf(e) - m);
+          if (e > m) mlo[s] |= bit;
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+          const float w = fmaxf(fminf(q.y, d[s].x2) - fmaxf(q.x, d[s].x1), 0.0f);
+          const float h = fmaxf(fminf(q.w, d[s].y2) - fmaxf(q.z, d[s].y1), 0.0f);
+          const float inter = w * h;
+          const float uni = (garea + d[s].area) - inter;
+          const float e = fmaf(uni, nthr, inter), m = uni * eps;
+          amb = fminf(amb, fabsf(e) - m);
+          if (e > m) mhi[s] |= bit;
+        }
+      }
+    }
+    const bool unsure = !(amb > 0.0f);
+    if (__any_sync(0xffffffffu, unsure) || n_slow > 0) {
+      const int n_exact = n_slow + (unsure ? n_fast : 0);
+      for (int i = 0; i < n_exact; ++i) {          // exact path: borderline pairs, exotic rows / thresholds
+        const int g = i < n_slow ? sh.gt_slow[i] : sh.gt_fast[i - n_slow];
+        const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
+        const float garea = gts[g].area;
+        const uint32_t bit = 1u << (g & 31);
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+          const float w = fmaxf(fminf(q.y, d[s].x2) - fmaxf(q.x, d[s].x1), 0.0f);
+          const float h = fmaxf(fminf(q.w, d[s].y2) - fmaxf(q.z, d[s].y1), 0.0f);
+          const float inter = w * h;
+          const float val = garea > 0.0f ? __fdiv_rn(inter, (garea + d[s].area) - inter) : garea;     // ssd.py:250
+          const bool hit = val > band.thr;
+          if (g < 32) mlo[s] = hit ? (mlo[s] | bit) : (mlo[s] & ~bit);
+          else mhi[s] = hit ? (mhi[s] | bit) : (mhi[s] & ~bit);
+        }
       }
     }
   }
-  {
-    int c = 0;
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) c += (valid[s] && mask[s] != 0ull) ? 1 : 0;
-    c = warp_sum(c);
-    if (lane == 0 && c) atomicAdd(&sh.pos_local, c);
-  }
-  if (!p.bulk) __syncthreads();
+  trace_point(p, 3);
 
   // ---- per-row terms ----------------------------------------------------------------------------------
+  // ce: positive CE (matched rows) or negative CE (unmatched rows); lloc: smooth-L1 sum; lse: log-sum-exp.
+  // Matched rows leave sum_g clamp(l - g_hat, -1, 1) -- the localisation gradient -- in their offset columns.
   float ce[kSlots], lloc[kSlots], lse[kSlots];
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) {
     ce[s] = 0.0f; lloc[s] = 0.0f; lse[s] = 0.0f;
-    const int rows_s = min(kLossThreads, my_rows - s * kLossThreads);
-    if (rows_s <= 0) continue;                                      // uniform per CTA
-    if (p.bulk) mbar_wait(&sh.mbar[s], 0);
+    if (s * kSlotBlocks + warp >= my_blocks) continue;              // uniform per warp
+    if (p.bulk) mbar_wait(&sh.mbar[s][warp], 0);
+    if (s == 0) trace_point(p, 4);
     const int lr = s * kLossThreads + tid;
-    const float* rp = slab + static_cast<size_t>(lr) * row;
+    float* rp = slab + static_cast<size_t>(lr) * row;
     if (valid[s]) {
-      float mx = rp[4];
-      for (int c = 1; c < C; ++c) mx = fmaxf(mx, rp[4 + c]);
-      const float mxs = mx * kLog2e;
-      float sum = 0.0f;
-      for (int c = 0; c < C; ++c) sum += ex2_approx(fmaf(rp[4 + c], kLog2e, -mxs));
+      float mx, sum = 0.0f;
+      if (kC > 0) {
+        float x[kC > 0 ? kC : 1];
+#pragma unroll
+        for (int c = 0; c < kC; ++c) x[c] = rp[4 + c];
+        mx = x[0];
+#pragma unroll
+        for (int c = 1; c + 1 < kC; c += 2) mx = fmaxf(mx, fmaxf(x[c], x[c + 1]));       // FMNMX3
+        if ((kC & 1) == 0) mx = fmaxf(mx, x[kC - 1]);
+        const float nmxs = -(mx * kLog2e);
+        const unsigned long long l2 = pack2(kLog2e, kLog2e), m2 = pack2(nmxs, nmxs);
+        unsigned long long acc2 = pack2(0.0f, 0.0f);
+#pragma unroll
+        for (int c = 0; c + 1 < kC; c += 2) {                                             // FFMA2 / FADD2: two classes per slot
+          float a0, a1;
+          unpack2(ffma2(pack2(x[c], x[c + 1]), l2, m2), a0, a1);
+          acc2 = fadd2(acc2, pack2(ex2_approx(a0), ex2_approx(a1)));
+        }
+        float s0, s1;
+        unpack2(acc2, s0, s1);
+        sum = s0 + s1;
+        if (kC & 1) sum += ex2_approx(fmaf(x[kC - 1], kLog2e, nmxs));
+      } else {
+        mx = rp[4];
+        for (int c = 1; c < C; ++c) mx = fmaxf(mx, rp[4 + c]);
+        const float mxs = mx * kLog2e;
+        for (int c = 0; c < C; ++c) sum += ex2_approx(fmaf(rp[4 + c], kLog2e, -mxs));
+      }
       const float ls = logf(sum);
       lse[s] = mx + ls;
-      unsigned long long m = mask[s];
-      if (m == 0ull) {
-        ce[s] = ls - (rp[4] - mx);                                   // -log_softmax[void]   (ssd.py:212-215)
-      } else {
-        const float4 q = p.priors[row0 + lr];
-        const float ldw = logf(q.z), ldh = logf(q.w);
+      ce[s] = ls - (rp[4] - mx);                                     // -log_softmax[void]   (ssd.py:212-215)
+      if ((mlo[s] | mhi[s]) != 0u) {
+        const float4 q = pri[s];
+        const float ldw = __logf(q.z), ldh = __logf(q.w);             // offsets only feed loss values: fast math is ample
+        const float rdw = __frcp_rn(q.z), rdh = __frcp_rn(q.w);
         const float l0 = rp[0], l1 = rp[1], l2 = rp[2], l3 = rp[3];
-        float acc_ce = 0.0f, acc_loc = 0.0f;
-        while (m) {
-          const int g = __ffsll(static_cast<long long>(m)) - 1;
-          m &= m - 1;
-          const GtRec& r = gts[g];
-          if (r.label >= 0) {
-            acc_ce += ls - (rp[4 + r.label] - mx);                   // -log_softmax[label]  (ssd.py:208-209)
-          } else {
-            const float* tw = p.targets + (static_cast<size_t>(n) * G + g) * row + 4;
-            float dot = 0.0f;
-            for (int c = 0; c < C; ++c) dot += tw[c] * ((rp[4 + c] - mx) - ls);
-            acc_ce += -dot;
+        float acc_ce = 0.0f, acc_loc = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t m = half ? mhi[s] : mlo[s];
+          while (m) {
+            const int g = 32 * half + __ffs(m) - 1;
+            m &= m - 1;
+            const GtRec& r = gts[g];
+            if (r.label >= 0) {
+              acc_ce += ls - (rp[4 + r.label] - mx);                 // -log_softmax[label]  (ssd.py:208-209)
+            } else {
+              const float* tw = p.targets + (static_cast<size_t>(n) * G + g) * row + 4;
+              float dot = 0.0f;
+              for (int c = 0; c < C; ++c) dot += tw[c] * ((rp[4 + c] - mx) - ls);
+              acc_ce += -dot;
+            }
+            const float x0 = l0 - (r.cx - q.x) * rdw;                // l - g-hat (ssd.py:202-204, 267-270)
+            const float x1 = l1 - (r.cy - q.y) * rdh;
+            const float x2 = l2 - ((r.flags & 1) ? r.lw - ldw : r.lw);
+            const float x3 = l3 - ((r.flags & 2) ? r.lh - ldh : r.lh);
+            acc_loc += ((smooth_l1_f(x0) + smooth_l1_f(x1)) + smooth_l1_f(x2)) + smooth_l1_f(x3);
+            g0 += clamp1(x0); g1 += clamp1(x1); g2 += clamp1(x2); g3 += clamp1(x3);
           }
-          const float e0 = __fdiv_rn(r.cx - q.x, q.z);               // g-hat (ssd.py:267-270)
-          const float e1 = __fdiv_rn(r.cy - q.y, q.w);
-          const float e2 = (r.flags & 1) ? r.lw - ldw : r.lw;
-          const float e3 = (r.flags & 2) ? r.lh - ldh : r.lh;
-          acc_loc += ((smooth_l1_f(l0 - e0) + smooth_l1_f(l1 - e1)) + smooth_l1_f(l2 - e2)) + smooth_l1_f(l3 - e3);
         }
         ce[s] = acc_ce;
         lloc[s] = acc_loc;
+        rp[0] = g0; rp[1] = g1; rp[2] = g2; rp[3] = g3;
       }
     }
-    hist_add(&sh.hist[0][0][0], valid[s], mask[s] != 0ull ? 0 : 1, float_key(ce[s]) >> 24, lane);
+    if (valid[s]) {
+      const uint32_t b = bucket_of(float_key(ce[s]));
+      atomicAdd(&sh.hist[0][(mlo[s] | mhi[s]) != 0u ? 0 : 1][b >> 1], 1u << (16 * (b & 1u)));
+    }
   }
 
-  // ---- cluster exchange #1: positives + pass-0 histograms of both sets --------------------------------------
+  {
+    int c = 0;
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) c += (valid[s] && (mlo[s] | mhi[s]) != 0u) ? 1 : 0;
+    c = warp_sum(c);
+    if (lane == 0 && c) atomicAdd(&sh.pos_local, c);
+  }
+
+  // ---- cluster exchange #1: positives + bucket histograms of both sets -----------------------------------------
+  trace_point(p, 5);
   cluster.sync();
+  trace_point(p, 6);
   if (tid < 256) {
     const int set = tid >> 7, w = tid & 127;
     uint32_t t = 0;
@@ -356,158 +555,156 @@ __global__ void __launch_bounds__(kLossThreads, 2) multibox_loss_kernel(const Lo
     if (lane == 0) {
       sh.k_pos = k_pos; sh.k_neg = k_neg;
       sh.sel_set = set; sh.need_select = set >= 0;
-      sh.sel_prefix = static_cast<uint32_t>(bin) << 24;
-      sh.sel_rem = rem;
+      sh.sel_prefix = static_cast<uint32_t>(bin);       // selected bucket
+      sh.sel_rem = rem;                                 // rank of the answer inside the bucket
     }
   }
   __syncthreads();
+  // The local radix passes reuse hist[1][*] (never touched outside the fallback) and tot[*] as their four zeroed
+  // histograms; tot is free from here on (the cluster barrier below orders this clear before its reuse).
+  if (tid < 256) (&sh.tot[0][0])[tid] = 0u;
+  trace_point(p, 7);
 
   const int sel_set = sh.sel_set;
-  if (sh.need_select) {
-    for (int pass = 1; pass < 4; ++pass) {
-      const int shift = 24 - 8 * pass;
-      const int buf = pass & 1;
-      const uint32_t prefix = sh.sel_prefix;
-      const uint32_t himask = 0xffffffffu << (shift + 8);
+  const bool need_select = sh.need_select != 0;
+  uint32_t sel_key = 0;          // order key of the searched threshold (identical in every thread of the cluster)
+  if (need_select) {
+    // my candidates of the selected bucket -> sh.list (order is irrelevant)
+    const uint32_t bucket = sh.sel_prefix;
 #pragma unroll
-      for (int s = 0; s < kSlots; ++s) {
-        if (min(kLossThreads, my_rows - s * kLossThreads) <= 0) continue;
-        const uint32_t key = float_key(ce[s]);
-        const bool member = valid[s] && ((mask[s] != 0ull) == (sel_set == 0)) && ((key & himask) == prefix);
-        hist_add(&sh.hist[buf][0][0], member, sel_set, (key >> shift) & 255u, lane);
-      }
-      cluster.sync();
-      if (tid < 128) {
-        uint32_t t = 0;
-#pragma unroll
-        for (int r = 0; r < kCluster; ++r) t += *cluster.map_shared_rank(&sh.hist[buf][sel_set][tid], r);
-        sh.tot[0][tid] = t;
-      } else {
-        (&sh.hist[buf ^ 1][0][0])[tid - 128] = 0u;      // 256 threads clear the other buffer for the next pass
-      }
-      __syncthreads();
-      if (warp == 0) {
-        uint32_t rem = sh.sel_rem;
-        const int bin = find_bin_desc(sh.tot[0], rem, lane);
-        if (lane == 0) {
-          sh.sel_prefix = prefix | (static_cast<uint32_t>(bin) << shift);
-          sh.sel_rem = rem;
-        }
-      }
-      __syncthreads();
+    for (int s = 0; s < kSlots; ++s) {
+      if (s * kSlotBlocks + warp >= my_blocks) continue;           // uniform per warp
+      const uint32_t key = float_key(ce[s]);
+      const bool member = valid[s] && (((mlo[s] | mhi[s]) != 0u) == (sel_set == 0)) && (bucket_of(key) == bucket);
+      const uint32_t ballot = __ballot_sync(0xffffffffu, member);
+      int base = 0;
+      if (lane == 0 && ballot) base = atomicAdd(&sh.list_cnt, __popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int pos = base + __popc(ballot & lt_mask);
+      if (member && pos < kListCap) sh.list[pos] = key;
     }
+    trace_point(p, 16);
+    cluster.sync();
+    trace_point(p, 17);
+    // everyone gathers every CTA's candidates and finishes the order statistic locally
+    int cnt[kCluster], total = 0;
+    bool over = false;
+#pragma unroll
+    for (int r = 0; r < kCluster; ++r) {
+      cnt[r] = *cluster.map_shared_rank(&sh.list_cnt, r);
+      over |= cnt[r] > kListCap;
+      total += cnt[r];
+    }
+    over |= total > kGatherCap;
+    uint32_t prefix = 0, rem = sh.sel_rem;
+    if (!over) {
+      for (int i = tid; i < total; i += kLossThreads) {
+        int r = 0, off = i;
+#pragma unroll
+        for (int q = 0; q < kCluster - 1; ++q)
+          if (r == q && off >= cnt[q]) { off -= cnt[q]; r = q + 1; }
+        sh.gathered[i] = cluster.map_shared_rank(&sh.list[0], r)[off];
+      }
+      __syncthreads();
+      trace_point(p, 18);
+      // Interior buckets pin the top 13 bits of the key: 19 bits remain -> 3 passes (8 + 8 + 3); the two clamped
+      // end buckets span arbitrary keys -> 4 full passes.  One buffer per pass, one barrier per pass; every warp
+      // resolves the bin redundantly from the same histogram.
+      const bool interior = bucket > 0u && bucket < 255u;
+      const int n_pass = interior ? 3 : 4;
+      if (interior) prefix = (bucket + 4096u + ((127u - 12u) << 4)) << 19;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int shift = interior ? (pass == 0 ? 11 : (pass == 1 ? 3 : 0)) : 24 - 8 * pass;
+        const int bits = (interior && pass == 2) ? 3 : 8;
+        const uint32_t himask = (shift + bits >= 32) ? 0u : (0xffffffffu << (shift + bits));
+        uint32_t* lh = pass < 2 ? &sh.hist[1][pass][0] : &sh.tot[pass - 2][0];
+        for (int i = tid; i < total; i += kLossThreads) {
+          const uint32_t key = sh.gathered[i];
+          if ((key & himask) == prefix) {
+            const uint32_t bin = (key >> shift) & ((1u << bits) - 1u);
+            atomicAdd(&lh[bin >> 1], 1u << (16 * (bin & 1u)));
+          }
+        }
+        __syncthreads();
+        const int bin = find_bin_desc(lh, rem, lane);
+        prefix |= static_cast<uint32_t>(bin) << shift;
+      }
+    } else {
+      // fallback (a bucket with more than kGatherCap candidates, e.g. thousands of identical CEs):
+      // cluster-wide 4-pass radix select on the full key through distributed shared memory
+      for (int i = tid; i < 2 * 2 * 128; i += kLossThreads) (&sh.hist[0][0][0])[i] = 0u;
+      __syncthreads();
+      rem = static_cast<uint32_t>(sel_set == 0 ? sh.k_pos : sh.k_neg);
+      for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const int buf = pass & 1;
+        const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+          if (s * kSlotBlocks + warp >= my_blocks) continue;
+          const uint32_t key = float_key(ce[s]);
+          const bool member = valid[s] && (((mlo[s] | mhi[s]) != 0u) == (sel_set == 0)) && ((key & himask) == prefix);
+          hist_add(&sh.hist[buf][0][0], member, sel_set, (key >> shift) & 255u, lane);
+        }
+        cluster.sync();
+        if (tid < 128) {
+          uint32_t t = 0;
+#pragma unroll
+          for (int r = 0; r < kCluster; ++r) t += *cluster.map_shared_rank(&sh.hist[buf][sel_set][tid], r);
+          sh.tot[0][tid] = t;
+        } else if (tid < 384) {
+          (&sh.hist[buf ^ 1][0][0])[tid - 128] = 0u;
+        }
+        __syncthreads();
+        const int bin = find_bin_desc(sh.tot[0], rem, lane);
+        prefix |= static_cast<uint32_t>(bin) << shift;
+        __syncthreads();
+      }
+    }
+    sel_key = prefix;
+    if (tid == 0) sh.overflow = over;
   }
-  const float thr_sel = sh.need_select ? key_float(sh.sel_prefix) : 0.0f;
+  trace_point(p, 8);
+  const float thr_sel = need_select ? key_float(sel_key) : 0.0f;
   const float thr_pos = sel_set == 0 ? thr_sel : 0.0f;
   const float thr_neg = sel_set == 1 ? thr_sel : 0.0f;
   const int k_pos = sh.k_pos;
   const float inv_pos = k_pos > 0 ? __fdiv_rn(1.0f, static_cast<float>(k_pos)) : 0.0f;     // ssd.py:226
 
   // ---- masked sums (ssd.py:227) ---------------------------------------------------------------------------
+  bool sel[kSlots];
   {
-    double acc = 0.0;
-    int npos = 0, nneg = 0;
+    float accf = 0.0f;
+    int cnt2 = 0;                            // selected positives | selected negatives << 16
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
-      if (!valid[s]) continue;
-      if (mask[s] != 0ull) {
-        if (ce[s] > thr_pos) { acc += static_cast<double>(p.a * lloc[s] + ce[s]); ++npos; }
-      } else if (ce[s] > thr_neg) {
-        acc += static_cast<double>(ce[s]);
-        ++nneg;
+      const bool pos = (mlo[s] | mhi[s]) != 0u;
+      sel[s] = valid[s] && (ce[s] > (pos ? thr_pos : thr_neg));
+      if (sel[s]) {
+        accf += pos ? (p.a * lloc[s] + ce[s]) : ce[s];
+        cnt2 += pos ? 1 : 65536;
       }
     }
-    acc = warp_sum(acc);
-    npos = warp_sum(npos);
-    nneg = warp_sum(nneg);
-    if (lane == 0) { sh.wred_loss[warp] = acc; sh.wred_a[warp] = npos; sh.wred_b[warp] = nneg; }
+    const double acc = warp_sum(static_cast<double>(accf));
+    cnt2 = warp_sum(cnt2);
+    if (lane == 0) { sh.wred_loss[warp] = acc; sh.wred_a[warp] = cnt2; }
     __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      int a2 = 0, b2 = 0;
-      for (int w = 0; w < kLossWarps; ++w) { t += sh.wred_loss[w]; a2 += sh.wred_a[w]; b2 += sh.wred_b[w]; }
-      *cluster.map_shared_rank(&sh.part_loss[rank], 0) = t;
-      *cluster.map_shared_rank(&sh.part_pos_sel[rank], 0) = a2;
-      *cluster.map_shared_rank(&sh.part_neg_sel[rank], 0) = b2;
-    }
-  }
-
-  // ---- gradient rows, in place over the slab, then out by TMA -------------------------------------------------
-  if (p.grad != nullptr) {
-    const float sn = inv_pos * p.inv_n_global;          // d loss / d (per-image sum)
-    float* dst = p.grad + (static_cast<size_t>(n) * p.P + row0) * row;
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-      const int rows_s = min(kLossThreads, my_rows - s * kLossThreads);
-      if (rows_s <= 0) continue;
-      const int lr = s * kLossThreads + tid;
-      float* rp = slab + static_cast<size_t>(lr) * row;
-      if (valid[s]) {
-        unsigned long long m = mask[s];
-        const bool sel_p = (m != 0ull) && (ce[s] > thr_pos);
-        const bool sel_n = (m == 0ull) && (ce[s] > thr_neg);
-        if (sel_n) {
-          const float ls2 = lse[s] * kLog2e;
-          for (int c = 0; c < C; ++c) rp[4 + c] = sn * ex2_approx(fmaf(rp[4 + c], kLog2e, -ls2));
-          rp[4] -= sn;
-          rp[0] = 0.0f; rp[1] = 0.0f; rp[2] = 0.0f; rp[3] = 0.0f;
-        } else if (sel_p) {
-          const float4 q = p.priors[row0 + lr];
-          const float ldw = logf(q.z), ldh = logf(q.w);
-          const float l0 = rp[0], l1 = rp[1], l2 = rp[2], l3 = rp[3];
-          float tsum = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
-          unsigned long long m2 = m;
-          while (m2) {
-            const int g = __ffsll(static_cast<long long>(m2)) - 1;
-            m2 &= m2 - 1;
-            const GtRec& r = gts[g];
-            tsum += r.tsum;
-            const float e0 = __fdiv_rn(r.cx - q.x, q.z);
-            const float e1 = __fdiv_rn(r.cy - q.y, q.w);
-            const float e2 = (r.flags & 1) ? r.lw - ldw : r.lw;
-            const float e3 = (r.flags & 2) ? r.lh - ldh : r.lh;
-            g0 += fminf(fmaxf(l0 - e0, -1.0f), 1.0f);
-            g1 += fminf(fmaxf(l1 - e1, -1.0f), 1.0f);
-            g2 += fminf(fmaxf(l2 - e2, -1.0f), 1.0f);
-            g3 += fminf(fmaxf(l3 - e3, -1.0f), 1.0f);
-          }
-          const float ls2 = lse[s] * kLog2e;
-          const float st = sn * tsum;
-          for (int c = 0; c < C; ++c) rp[4 + c] = st * ex2_approx(fmaf(rp[4 + c], kLog2e, -ls2));
-          while (m) {
-            const int g = __ffsll(static_cast<long long>(m)) - 1;
-            m &= m - 1;
-            const GtRec& r = gts[g];
-            if (r.label >= 0) {
-              rp[4 + r.label] -= sn;
-            } else {
-              const float* tw = p.targets + (static_cast<size_t>(n) * G + g) * row + 4;
-              for (int c = 0; c < C; ++c) rp[4 + c] -= sn * tw[c];
-            }
-          }
-          const float as = p.a * sn;
-          rp[0] = as * g0; rp[1] = as * g1; rp[2] = as * g2; rp[3] = as * g3;
-        } else {
-          for (int c = 0; c < row; ++c) rp[c] = 0.0f;
-        }
+    if (warp == 0) {
+      double t = lane < kLossWarps ? sh.wred_loss[lane] : 0.0;
+      int c2 = lane < kLossWarps ? sh.wred_a[lane] : 0;
+      t = warp_sum(t);                      // fixed shuffle tree: deterministic
+      c2 = warp_sum(c2);
+      if (lane == 0) {
+        *cluster.map_shared_rank(&sh.part_loss[rank], 0) = t;
+        *cluster.map_shared_rank(&sh.part_pos_sel[rank], 0) = c2 & 0xffff;
+        *cluster.map_shared_rank(&sh.part_neg_sel[rank], 0) = c2 >> 16;
       }
-      if (p.bulk) {
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0)
-          bulk_store(dst + static_cast<size_t>(s) * kLossThreads * row, slab + static_cast<size_t>(s) * kLossThreads * row,
-                     static_cast<uint32_t>(rows_s) * row * sizeof(float));
-      }
-    }
-    if (!p.bulk) {
-      __syncthreads();
-      const int total = my_rows * row;
-      for (int i = tid; i < total; i += kLossThreads) dst[i] = slab[i];
     }
   }
 
   // ---- cluster exchange #2: per-image loss, stats, batch mean ----------------------------------------------------
-  cluster.sync();
+  cluster.sync();          // last use of distributed shared memory: CTAs are independent from here on
+  trace_point(p, 9);
   if (rank == 0 && tid == 0) {
     double total = 0.0;
     int pos_sel = 0, neg_sel = 0;
@@ -530,8 +727,95 @@ __global__ void __launch_bounds__(kLossThreads, 2) multibox_loss_kernel(const Lo
       *p.ticket = 0u;
     }
   }
-  if (p.bulk && p.grad != nullptr && tid == 0) bulk_store_wait();
+  // ---- gradient rows, in place over the slab, then out by TMA -------------------------------------------------
+  if (p.grad != nullptr) {
+    const float sn = inv_pos * p.inv_n_global;          // d loss / d (per-image sum)
+    float* img_out = p.grad + static_cast<size_t>(n) * p.P * row;
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+      const int j = s * kSlotBlocks + warp;
+      if (j >= my_blocks) continue;                                 // uniform per warp
+      const int lr = s * kLossThreads + tid;
+      float* rp = slab + static_cast<size_t>(lr) * row;
+      // One code path for every lane: row <- scale * softmax(row) with scale = s_n * (sum of matched class weights)
+      // for a selected positive, s_n for a selected negative and 0 for an unselected row (exact zeros); then the
+      // one-hot corrections.  Warps without any selected row (the common case late in training) just clear.
+      if (!__any_sync(0xffffffffu, sel[s])) {
+        if (valid[s])
+          for (int c = 0; c < row; ++c) rp[c] = 0.0f;
+      } else if (valid[s]) {
+        const bool pos = (mlo[s] | mhi[s]) != 0u;
+        float tsum = 1.0f;
+        if (pos) {
+          if (!sh.soft_labels) {
+            tsum = static_cast<float>(__popc(mlo[s]) + __popc(mhi[s]));
+          } else {
+            tsum = 0.0f;
+            for (int half = 0; half < 2; ++half) {
+              uint32_t m = half ? mhi[s] : mlo[s];
+              while (m) { tsum += gts[32 * half + __ffs(m) - 1].tsum; m &= m - 1; }
+            }
+          }
+        }
+        softmax_scaled<kC>(rp + 4, C, lse[s], sel[s] ? sn * tsum : 0.0f);
+        const float as = (sel[s] && pos) ? p.a * sn : 0.0f;       // offset columns of matched rows hold sum_g clamp(l - g_hat)
+        rp[0] *= as; rp[1] *= as; rp[2] *= as; rp[3] *= as;
+        if (sel[s]) {
+          if (!pos) {
+            rp[4] -= sn;
+          } else {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t m = half ? mhi[s] : mlo[s];
+              while (m) {
+                const int g = 32 * half + __ffs(m) - 1;
+                m &= m - 1;
+                const int label = gts[g].label;
+                if (label >= 0) {
+                  rp[4 + label] -= sn;
+                } else {
+                  const float* tw = p.targets + (static_cast<size_t>(n) * G + g) * row + 4;
+                  for (int c = 0; c < C; ++c) rp[4 + c] -= sn * tw[c];
+                }
+              }
+            }
+          }
+        }
+      }
+      const int gb = j * kCluster + rank;
+      const int rows_b = min(kBlockRows, p.P - gb * kBlockRows);
+      float* dst = img_out + static_cast<size_t>(gb) * kBlockRows * row;
+      const float* srcb = slab + static_cast<size_t>(j) * kBlockRows * row;
+      if (p.bulk) {
+        fence_async_smem();               // my generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          bulk_store(dst, srcb, static_cast<uint32_t>(rows_b) * row * sizeof(float));
+          bulk_store_commit();
+        }
+      } else {
+        __syncwarp();
+        for (int i = lane; i < rows_b * row; i += 32) dst[i] = srcb[i];
+      }
+    }
+  }
+
+  trace_point(p, 10);
+  if (p.bulk && p.grad != nullptr && lane == 0) bulk_store_wait();
+  trace_point(p, 11);
+  trace_point(p, 12);
+  if (p.trace != nullptr && tid == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 13] = smid;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 14] = t;
+    p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 15] = static_cast<unsigned long long>(sh.overflow);
+  }
 }
+
+static unsigned long long* g_loss_trace = nullptr;
 
 static size_t loss_smem_bytes(int rows_per_cta, int row, int G) {
   const size_t slab = (static_cast<size_t>(rows_per_cta) * row * sizeof(float) + 15) & ~static_cast<size_t>(15);
@@ -539,36 +823,61 @@ static size_t loss_smem_bytes(int rows_per_cta, int row, int G) {
   return slab + gt + sizeof(LossShared);
 }
 
-static int rows_per_cta_for(int P) {
-  const int r = (P + kCluster - 1) / kCluster;
-  return (r + 3) & ~3;
+static int blocks_for(int P) { return (P + kBlockRows - 1) / kBlockRows; }
+
+static int rows_per_cta_for(int P, int cluster) {          // shared-memory rows of the busiest CTA
+  return ((blocks_for(P) + cluster - 1) / cluster) * kBlockRows;
 }
 
-template <int kC>
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
+// Which kernel shape serves (P, C, G): 4 CTAs x 768 threads when the quarter slab fits one SM, else 8 x 384.
+struct LossShape { int cluster, threads, rows_per_cta; size_t smem; };
+
+static bool pick_shape(int P, int C, int G, LossShape* out) {
+  static const int forced = [] { const char* e = getenv("SSDH_LOSS_CLUSTER"); return e ? atoi(e) : 0; }();
+  const int row = 4 + C;
+  const int shapes[2][2] = {{4, 768}, {8, 384}};
+  for (int i = 0; i < 2; ++i) {
+    if (forced && shapes[i][0] != forced) continue;
+    LossShape s;
+    s.cluster = shapes[i][0]; s.threads = shapes[i][1];
+    s.rows_per_cta = rows_per_cta_for(P, s.cluster);
+    s.smem = loss_smem_bytes(s.rows_per_cta, row, G);
+    if (s.rows_per_cta <= kSlots * s.threads && s.smem <= kMaxDynSmem) { *out = s; return true; }
+  }
+  return false;
+}
+
+template <int kC, int kT, int kCl>
 static int launch_loss(const LossParams& p, size_t smem, cudaStream_t st) {
-  static bool configured = false;     // per instantiation; attribute is sticky per device context
-  static size_t configured_smem = 0;
-  if (!configured || smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(multibox_loss_kernel<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(227 * 1024));
+  static bool configured = false;     // per instantiation; one process drives one device
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(multibox_loss_kernel<kC, kT, kCl>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
     if (e != cudaSuccess) { set_error("ssdh_multibox_loss: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
     configured = true;
-    configured_smem = 227 * 1024;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(p.N) * kCluster);
-  cfg.blockDim = dim3(kLossThreads);
+  cfg.gridDim = dim3(static_cast<unsigned>(p.N) * kCl);
+  cfg.blockDim = dim3(kT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.x = kCl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, multibox_loss_kernel<kC>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, multibox_loss_kernel<kC, kT, kCl>, p);
   if (e != cudaSuccess) { set_error("ssdh_multibox_loss: launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
   return 0;
+}
+
+template <int kC>
+static int launch_loss_shape(const LossParams& p, const LossShape& s, cudaStream_t st) {
+  if (s.cluster == 4) return launch_loss<kC, 768, 4>(p, s.smem, st);
+  return launch_loss<kC, 384, 8>(p, s.smem, st);
 }
 
 }  // namespace ssdh
@@ -594,13 +903,12 @@ extern "C" int ssdh_multibox_loss(const float* outputs, const float* targets, co
   if (!ws || ws_bytes < ssdh_multibox_loss_workspace_bytes(N, P, C, G)) { set_error("ssdh_multibox_loss: workspace too small"); return SSDH_E_WORKSPACE; }
   if (!aligned16(priors) || !aligned16(ws)) { set_error("ssdh_multibox_loss: priors and ws must be 16-byte aligned"); return SSDH_E_ALIGN; }
   const int row = 4 + C;
-  const int rpc = rows_per_cta_for(P);
-  if (rpc > kSlots * kLossThreads) {
-    set_error("ssdh_multibox_loss: P=%d needs %d rows per CTA, limit %d", P, rpc, kSlots * kLossThreads);
+  LossShape shape;
+  if (!pick_shape(P, C, G, &shape)) {
+    set_error("ssdh_multibox_loss: one image's [P=%d, %d] slab does not fit a cluster's shared memory (8 x ~220 KB, %d rows per CTA)",
+              P, row, kSlots * 384);
     return SSDH_E_LIMIT;
   }
-  const size_t smem = loss_smem_bytes(rpc, row, G);
-  if (smem > 227 * 1024) { set_error("ssdh_multibox_loss: image slab of %zu bytes per CTA exceeds shared memory", smem); return SSDH_E_LIMIT; }
 
   LossParams p;
   p.outputs = outputs; p.targets = targets; p.priors = reinterpret_cast<const float4*>(priors);
@@ -610,14 +918,19 @@ extern "C" int ssdh_multibox_loss(const float* outputs, const float* targets, co
   p.loss = loss; p.grad = grad; p.stats = stats;
   p.ticket = reinterpret_cast<unsigned int*>(ws);
   p.image_loss = reinterpret_cast<double*>(static_cast<unsigned char*>(ws) + 16);
-  p.rows_per_cta = rpc;
+  p.rows_per_cta = shape.rows_per_cta;
+  p.n_blocks = blocks_for(P);
   // TMA bulk copies need 16-byte aligned addresses and sizes for every (image, CTA, slot) chunk.
-  const bool sizes_ok = (static_cast<long long>(P) * row) % 4 == 0;     // rpc and the slot size are multiples of 4 rows
+  const bool sizes_ok = (static_cast<long long>(P) * row) % 4 == 0;     // full blocks are 32 rows; only the tail block can be odd
   p.bulk = sizes_ok && aligned16(outputs) && (grad == nullptr || aligned16(grad));
+  p.trace = g_loss_trace;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (C == 21) return launch_loss<21>(p, smem, st);
-  return launch_loss<0>(p, smem, st);
+  if (C == 21) return launch_loss_shape<21>(p, shape, st);
+  return launch_loss_shape<0>(p, shape, st);
 }
+
+// Debug hook (not part of the public header): device buffer of [N * 8][16] u64 phase stamps, or NULL to disable.
+extern "C" __attribute__((visibility("default"))) void ssdh_debug_set_loss_trace(unsigned long long* buf) { g_loss_trace = buf; }
 
 extern "C" int ssdh_device_info(int* sm_count, int* max_smem_optin, int* loss_cluster_size, int* loss_max_active_clusters) {
   int dev = 0;
@@ -628,19 +941,26 @@ extern "C" int ssdh_device_info(int* sm_count, int* max_smem_optin, int* loss_cl
   if (e != cudaSuccess) { set_error("ssdh_device_info: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
   if (sm_count) *sm_count = prop.multiProcessorCount;
   if (max_smem_optin) *max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
-  if (loss_cluster_size) *loss_cluster_size = kCluster;
+  LossShape shape;
+  pick_shape(SSDH_NUM_PRIORS, 21, 20, &shape);
+  if (loss_cluster_size) *loss_cluster_size = shape.cluster;
   if (loss_max_active_clusters) {
-    cudaFuncSetAttribute(multibox_loss_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kCluster * 64);
-    cfg.blockDim = dim3(kLossThreads);
-    cfg.dynamicSmemBytes = loss_smem_bytes(rows_per_cta_for(SSDH_NUM_PRIORS), 25, 20);
+    cfg.gridDim = dim3(shape.cluster * 64);
+    cfg.blockDim = dim3(shape.threads);
+    cfg.dynamicSmemBytes = shape.smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = shape.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int nc = 0;
-    e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21>, &cfg);
+    if (shape.cluster == 4) {
+      cudaFuncSetAttribute(multibox_loss_kernel<21, 768, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
+      e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 768, 4>, &cfg);
+    } else {
+      cudaFuncSetAttribute(multibox_loss_kernel<21, 384, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
+      e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 384, 8>, &cfg);
+    }
     if (e != cudaSuccess) { set_error("ssdh_device_info: occupancy: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
     *loss_max_active_clusters = nc;
   }

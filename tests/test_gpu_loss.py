@@ -34,7 +34,7 @@ def test_default_boxes_bit_exact(golden, priors_cpu, priors_gpu):
 
 def test_device_info():
     info = ops.device_info()
-    assert info["sm_count"] >= 100 and info["loss_cluster_size"] == 8 and info["loss_max_active_clusters"] >= 1
+    assert info["sm_count"] >= 100 and info["loss_cluster_size"] in (4, 8) and info["loss_max_active_clusters"] >= 1
 
 
 @pytest.mark.parametrize("case", cases.LOSS_CASES, ids=[c[0] for c in cases.LOSS_CASES])
