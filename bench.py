@@ -307,31 +307,47 @@ def main():
 
 
 def bench_post(ops, synth, priors, dev, peak):
-    """configs[2]: batch-256 inference post-processing (decode + score + NMS fused, in place), trained-like logits D2."""
+    """configs[2]: batch-256 inference post-processing (decode + score + NMS fused, in place).  D2 = trained-like
+    logits (a few hundred candidates per image, HBM-bound), D1 = random-init logits (~8 300 candidates per image, the
+    greedy suppression is fp32-compute-bound by construction -- SURVEY 7.3-4).  Each call is replayed from a CUDA
+    graph (3 kernels, no host gaps) on a freshly restored input; the restore copy is outside the timed region."""
     res = {}
-    for dist_name, reps in (("D2", 20), ("D1", 2)):
+    for dist_name, reps in (("D2", 20), ("D1", 3)):
         n = POST_BATCH if dist_name == "D2" else 32
         src = synth.make_outputs(n, 5, dist_name).to(dev)
         bufs = [src.clone() for _ in range(2 if dist_name == "D2" else 1)]        # 2 x 224 MB > L2
-        for b in bufs:
-            ops.postprocess_(b, priors, iou_thresh=0.45)
+        order = torch.empty(n, P, dtype=torch.int32, device=dev)
+        graphs = []
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for b in bufs:
+                out = ops.postprocess_(b, priors, iou_thresh=0.45, want_lists=True)      # warm-up + workspace allocation
+                b.copy_(src)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    out = ops.postprocess_(b, priors, iou_thresh=0.45, want_lists=True)
+                graphs.append((g, out))
+        torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         times = []
-        for r in range(reps):
+        for r in range(reps + 3):
             b = bufs[r % len(bufs)]
+            g, out = graphs[r % len(bufs)]
             b.copy_(src)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = ops.postprocess_(b, priors, iou_thresh=0.45, want_lists=True)
+            g.replay()
             e1.record()
             torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
+            if r >= 3:
+                times.append(e0.elapsed_time(e1))
         ms = statistics.median(times)
         alg = n * 2 * SLAB
         res[dist_name] = {"batch": n, "ms": ms, "images_per_s": n / (ms * 1e-3), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
                           "candidates_per_image": float(out.order_cnt.float().mean()), "kept_per_image": float(out.keep_cnt.float().mean()),
-                          "launches_per_call": 2}
+                          "launches_per_call": 3}
     return res
 
 

@@ -170,6 +170,7 @@ struct NmsParams {
   int32_t* order_cnt;         // [N] or NULL
   int32_t* keep;              // [N, P] (workspace or user)
   int32_t* keep_cnt;          // [N] or NULL
+  unsigned long long* trace;  // debug: [N][16] SM clock stamps, NULL in production
 };
 
 struct NmsShared {
@@ -180,9 +181,10 @@ struct NmsShared {
   int n_cand, kept, uniform_digit, stop;
 };
 
-__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) {
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, const int32_t* __restrict__ large) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = blockIdx.x, P = p.P, row = 4 + p.C;
+  if (large != nullptr && large[n] == 0) return;          // already handled by nms_small_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
@@ -331,7 +333,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
     }
     // the sorted order leaves shared memory here; the kept list takes over the region
     for (int i = tid; i < K; i += kNmsThreads) order[i] = iin[i];
-    for (int i = K + tid; i < P; i += kNmsThreads) order[i] = -1;
     __syncthreads();
   }
 
@@ -423,7 +424,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
   }
   __syncthreads();
   const int kept = sh.kept;
-  for (int i = kept + tid; i < P; i += kNmsThreads) keep[i] = -1;
   if (tid == 0) {
     if (p.keep_cnt) p.keep_cnt[n] = kept;
     if (p.order_cnt) p.order_cnt[n] = K;
@@ -445,6 +445,326 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p) 
   }
 }
 
+
+// Branch-free pair test for the NMS inner loops.  Mirrors src/utils.py:74-77 followed by `> thr`:
+//   inter = clamp(w) * clamp(h);  value = inter > 0 ? inter / union : inter;  hit = value > thr.
+// e = inter - union * thr is a single FMA, so its sign is exact; when |e| clears the 2^-20 band the rounded
+// quotient is on the same side of thr with certainty.  Pairs inside the band (or with a degenerate union) report
+// `amb` and are settled by the caller with the IEEE division (iou_gt), which keeps keep-lists bit-identical.
+struct PairThr {
+  float thr, nthr, eps;
+  bool usable;
+};
+__host__ __device__ inline PairThr make_pair_thr(float thr) {
+  PairThr t;
+  t.thr = thr; t.nthr = -thr; t.eps = thr * 9.5367431640625e-07f;
+  t.usable = thr >= 1e-6f && thr <= 1e6f;
+  return t;
+}
+__device__ __forceinline__ bool pair_hit_fast(const float4 a, float a_area, const float4 b, float b_area, const PairThr& t, bool& amb) {
+  // boxes are (x1, x2, y1, y2)
+  const float w = fmaxf(fminf(a.y, b.y) - fmaxf(a.x, b.x), 0.0f);
+  const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.z, b.z), 0.0f);
+  const float inter = w * h;
+  const float uni = (a_area + b_area) - inter;
+  const float e = fmaf(uni, t.nthr, inter), m = uni * t.eps;
+  // inter == 0 gives e = -union * thr < -m for any sane union; a non-positive / non-finite union lands in the band
+  amb = !(fabsf(e) > m) || !(uni >= 1e-30f);
+  return e > m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NMS, small-K kernel: images with at most kSmallCap candidates (every realistic, trained-like image).
+// 512 threads, ~64 KB of shared memory -> three images per SM.  Same results as nms_kernel:
+//   compaction in row order -> stable radix sort -> K x K suppression bitmask built in parallel (warp per row,
+//   lane per column, ballot per 32 columns) -> one warp walks the rows in score order, OR-ing the masks of
+//   the rows it keeps into a register-resident `removed` bitset.
+// Images with more candidates are flagged in `large[]` and left to nms_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 512;
+constexpr int kSmallWarps = kSmallThreads / 32;
+constexpr int kSmallCap = 512;
+constexpr int kSmallWords = kSmallCap / 32;
+constexpr int kSmallRounds = 18;         // rows per lane in the compaction -> P <= 16 warps * 32 * 18 = 9216
+
+struct SmallShared {
+  uint32_t keys[2][kSmallCap];
+  uint16_t idx[2][kSmallCap];
+  uint16_t whist[kSmallWarps * 256];
+  int part[2][256];
+  int digit_base[256];
+  float4 box[kSmallCap];          // x1, x2, y1, y2 of the sorted candidates
+  float area[kSmallCap];
+  uint8_t cls[kSmallCap];
+  uint32_t ov_in[kSmallCap][kSmallWords];  // ov_in[j] bit i (i < j): an earlier (higher-score) candidate i overlaps j above the threshold
+  uint32_t kept_words[kSmallWords], supp_words[kSmallWords];
+  int undecided[2];
+  int warp_total[kSmallWarps];
+  int n_cand, uniform_digit, kept;
+};
+
+#define NMS_TRACE(idx) do { if (p.trace != nullptr && threadIdx.x == 0) p.trace[static_cast<size_t>(blockIdx.x) * 16 + (idx)] = clock64(); } while (0)
+static unsigned long long* g_nms_trace = nullptr;
+
+__global__ void __launch_bounds__(kSmallThreads, 3) nms_small_kernel(const NmsParams p, int32_t* __restrict__ large) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmallShared& sh = *reinterpret_cast<SmallShared*>(smem_raw);
+  uint32_t* keep_bits = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(SmallShared) + 15) & ~static_cast<size_t>(15)));   // P bits
+  const int n = blockIdx.x, P = p.P, row = 4 + p.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const float* key_in = p.cand_key + static_cast<size_t>(n) * P;
+  const uint8_t* cls_in = p.cand_cls + static_cast<size_t>(n) * P;
+  int32_t* order = p.order + static_cast<size_t>(n) * P;
+  int32_t* keep = p.keep + static_cast<size_t>(n) * P;
+  float* img = p.outputs + static_cast<size_t>(n) * P * row;
+
+  NMS_TRACE(0);
+  // ---- A. candidates in row order: warp w owns a contiguous chunk of rows; all of a lane's loads are issued before
+  // the first ballot so the chunk costs one memory latency, not one per 32 rows -----------------------------------------
+  const int chunk = ((P + kSmallWarps * 32 - 1) / (kSmallWarps * 32)) * 32;        // rows per warp, multiple of 32
+  const int c0 = warp * chunk, c1 = min(P, c0 + chunk);
+  float kv[kSmallRounds];
+#pragma unroll
+  for (int q = 0; q < kSmallRounds; ++q) {
+    const int r = c0 + 32 * q + lane;
+    kv[q] = (32 * q < chunk && r < c1) ? key_in[r] : 0.0f;
+  }
+  uint32_t cand_bits[kSmallRounds];
+  int mine = 0;                                    // warp-uniform count of candidates in my chunk
+#pragma unroll
+  for (int q = 0; q < kSmallRounds; ++q) {
+    cand_bits[q] = __ballot_sync(0xffffffffu, kv[q] > p.score_thr);
+    mine += __popc(cand_bits[q]);
+  }
+  if (lane == 0) sh.warp_total[warp] = mine;
+  for (int i = tid; i < kSmallCap * kSmallWords; i += kSmallThreads) (&sh.ov_in[0][0])[i] = 0u;
+  if (tid < kSmallWords) { sh.kept_words[tid] = 0u; sh.supp_words[tid] = 0u; }
+  if (tid < 2) sh.undecided[tid] = 0;
+  __syncthreads();
+  int before = 0, total = 0;
+  for (int w = 0; w < kSmallWarps; ++w) {
+    const int t = sh.warp_total[w];
+    before += w < warp ? t : 0;
+    total += t;
+  }
+  const int K = total;
+  if (K > kSmallCap) {                       // uniform: leave this image to the general kernel
+    if (tid == 0) large[n] = 1;
+    return;
+  }
+  if (tid == 0) large[n] = 0;
+#pragma unroll
+  for (int q = 0; q < kSmallRounds; ++q) {
+    if ((cand_bits[q] >> lane) & 1u) {
+      const int pos = before + __popc(cand_bits[q] & lt_mask);
+      sh.keys[0][pos] = ~float_key(kv[q]);
+      sh.idx[0][pos] = static_cast<uint16_t>(c0 + 32 * q + lane);
+    }
+    before += __popc(cand_bits[q]);
+  }
+  if (!p.scatter)
+    for (int i = tid; i < (P + 31) / 32; i += kSmallThreads) keep_bits[i] = 0u;
+  __syncthreads();
+
+  NMS_TRACE(1);
+  // ---- B. stable LSD radix sort, one key per thread -------------------------------------------------------------
+  int cur = 0;
+  for (int pass = 0; pass < 4 && K > 1; ++pass) {
+    const int shift = 8 * pass;
+    for (int i = tid; i < kSmallWarps * 256 / 2; i += kSmallThreads) reinterpret_cast<uint32_t*>(sh.whist)[i] = 0u;
+    __syncthreads();
+    uint16_t* my_hist = sh.whist + warp * 256;
+    const bool act = tid < K;
+    const uint32_t key = act ? sh.keys[cur][tid] : 0u;
+    const uint32_t d = act ? ((key >> shift) & 255u) : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (act && lane == __ffs(peers) - 1) my_hist[d] = static_cast<uint16_t>(__popc(peers));
+    const int loc = __popc(peers & lt_mask);
+    __syncthreads();
+    {
+      const int dd = tid & 255, q = tid >> 8;          // q handles warps [8q, 8q + 8)
+      int sum = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += sh.whist[(8 * q + w) * 256 + dd];
+      sh.part[q][dd] = sum;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int t[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        t[j] = sh.part[0][lane * 8 + j] + sh.part[1][lane * 8 + j];
+        sum += t[j];
+      }
+      const int inc = warp_incl_scan(sum, lane);
+      int run = inc - sum;
+      bool uni = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sh.digit_base[lane * 8 + j] = run;
+        run += t[j];
+        uni |= (t[j] == K);
+      }
+      const uint32_t any_uni = __ballot_sync(0xffffffffu, uni);
+      if (lane == 0) sh.uniform_digit = any_uni != 0u;
+    }
+    __syncthreads();
+    if (sh.uniform_digit) continue;                     // block-uniform; rewritten only two barriers later
+    {
+      const int dd = tid & 255, q = tid >> 8;
+      int run = sh.digit_base[dd] + (q ? sh.part[0][dd] : 0);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int c = sh.whist[(8 * q + w) * 256 + dd];
+        sh.whist[(8 * q + w) * 256 + dd] = static_cast<uint16_t>(run);
+        run += c;
+      }
+    }
+    __syncthreads();
+    if (act) {
+      const int pos = my_hist[d] + loc;
+      sh.keys[cur ^ 1][pos] = key;
+      sh.idx[cur ^ 1][pos] = sh.idx[cur][tid];
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+
+  NMS_TRACE(2);
+  // ---- sorted candidates: order list, boxes ---------------------------------------------------------------------
+  if (tid < K) {
+    const int r = sh.idx[cur][tid];
+    order[tid] = r;
+    const float* b = img + static_cast<size_t>(r) * row;
+    const Corners c = make_corners(b[0], b[1], b[2], b[3]);
+    sh.box[tid] = make_float4(c.x1, c.x2, c.y1, c.y2);
+    sh.area[tid] = c.area;
+    sh.cls[tid] = p.per_class ? cls_in[r] : 0;
+  }
+  __syncthreads();
+
+  NMS_TRACE(3);
+  // ---- C1. overlaps: warp per row i, lane per later column j; the (sparse) hits are recorded at the SUPPRESSED side,
+  // ov_in[j] |= bit i, which is the orientation the resolution below reads --------------------------------------------
+  const ThrBand band = p.band;
+  const PairThr pt = make_pair_thr(band.thr);
+  const int Kw = (K + 31) / 32;
+  for (int i = warp; i < K; i += kSmallWarps) {
+    const float4 bi = sh.box[i];
+    const float ai = sh.area[i];
+    const int ci = sh.cls[i];
+    const uint32_t ibit = 1u << (i & 31);
+    bool row_amb = !pt.usable;
+    for (int w = i >> 5; w < Kw; ++w) {
+      const int jj = 32 * w + lane;
+      const int j = min(jj, K - 1);
+      bool amb;
+      bool hit = pair_hit_fast(bi, ai, sh.box[j], sh.area[j], pt, amb);
+      row_amb |= amb;
+      if (p.per_class) hit = hit && sh.cls[j] == ci;
+      if (hit && jj > i && jj < K) atomicOr(&sh.ov_in[jj][i >> 5], ibit);
+    }
+    if (__any_sync(0xffffffffu, row_amb)) {          // rare: redo the row with the exact division (set or clear each bit)
+      Corners a;
+      a.x1 = bi.x; a.x2 = bi.y; a.y1 = bi.z; a.y2 = bi.w; a.area = ai;
+      for (int w = i >> 5; w < Kw; ++w) {
+        const int jj = 32 * w + lane;
+        if (jj > i && jj < K) {
+          const float4 bj = sh.box[jj];
+          Corners o;
+          o.x1 = bj.x; o.x2 = bj.y; o.y1 = bj.z; o.y2 = bj.w; o.area = sh.area[jj];
+          const bool hit = iou_gt(a, o, band) && (sh.cls[jj] == ci);
+          if (hit) atomicOr(&sh.ov_in[jj][i >> 5], ibit);
+          else atomicAnd(&sh.ov_in[jj][i >> 5], ~ibit);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  NMS_TRACE(4);
+  // ---- C2. greedy NMS as a parallel fixed point.  Candidate j (thread j) is
+  //   suppressed as soon as an earlier overlapping candidate is known kept,
+  //   kept       as soon as every earlier overlapping candidate is known suppressed.
+  // The first undecided candidate in score order always resolves, so each round makes progress; the result is exactly
+  // the sequential greedy keep set (src/utils.py:102-108).  Typical images settle in a handful of rounds. -----------------
+  {
+    int state = tid < K ? 0 : 2;             // 0 undecided, 1 kept, 2 suppressed / not a candidate
+    uint32_t in_w[kSmallWords];
+#pragma unroll
+    for (int w = 0; w < kSmallWords; ++w) in_w[w] = (tid < K && w < Kw) ? sh.ov_in[tid][w] : 0u;
+    for (int round = 0; round <= K; ++round) {
+      if (state == 0) {
+        bool any_kept = false, all_supp = true;
+#pragma unroll
+        for (int w = 0; w < kSmallWords; ++w) {
+          any_kept |= (in_w[w] & sh.kept_words[w]) != 0u;
+          all_supp &= (in_w[w] & ~sh.supp_words[w]) == 0u;
+        }
+        if (any_kept) state = 2;
+        else if (all_supp) state = 1;
+      }
+      __syncthreads();                        // everyone has read the word arrays (and the previous round's flag)
+      if (tid == 0) sh.undecided[(round + 1) & 1] = 0;
+      if (tid < K) {
+        const uint32_t bit = 1u << (tid & 31);
+        if (state == 1 && !(sh.kept_words[tid >> 5] & bit)) atomicOr(&sh.kept_words[tid >> 5], bit);
+        if (state == 2 && !(sh.supp_words[tid >> 5] & bit)) atomicOr(&sh.supp_words[tid >> 5], bit);
+        if (state == 0) sh.undecided[round & 1] = 1;
+      }
+      __syncthreads();
+      if (!sh.undecided[round & 1]) { if (p.trace != nullptr && tid == 0) p.trace[static_cast<size_t>(blockIdx.x) * 16 + 8] = round + 1; break; }    // block-uniform
+    }
+    if (tid == 0) {
+      int kept = 0;
+      for (int w = 0; w < Kw; ++w) kept += __popc(sh.kept_words[w]);
+      sh.kept = kept;
+    }
+    __syncthreads();
+    if (p.top_k > 0 && sh.kept > p.top_k) {   // keep only the first top_k kept candidates (block-uniform branch)
+      if (tid == 0) {
+        int left = p.top_k;
+        for (int w = 0; w < Kw; ++w) {
+          uint32_t bits = sh.kept_words[w], out = 0u;
+          while (bits && left > 0) { const uint32_t b = bits & (0u - bits); out |= b; bits ^= b; --left; }
+          sh.kept_words[w] = out;
+        }
+        sh.kept = p.top_k;
+      }
+      __syncthreads();
+    }
+  }
+
+  NMS_TRACE(5);
+  // ---- D. keep list (score order), counts, apply ----------------------------------------------------------------------
+  const int kept = sh.kept;
+  if (tid < K) {
+    const uint32_t wbits = sh.kept_words[tid >> 5];
+    if ((wbits >> (tid & 31)) & 1u) {
+      int pos = __popc(wbits & ((1u << (tid & 31)) - 1u));
+      for (int w = 0; w < (tid >> 5); ++w) pos += __popc(sh.kept_words[w]);
+      const int r = sh.idx[cur][tid];
+      keep[pos] = r;
+      if (p.scatter) img[static_cast<size_t>(r) * row + 4 + cls_in[r]] = key_in[r];
+      else atomicOr(&keep_bits[r >> 5], 1u << (r & 31));
+    }
+  }
+  if (tid == 0) {
+    if (p.keep_cnt) p.keep_cnt[n] = kept;
+    if (p.order_cnt) p.order_cnt[n] = K;
+  }
+  NMS_TRACE(6);
+  if (!p.scatter) {
+    __syncthreads();
+    for (int r = warp; r < P; r += kSmallWarps) {
+      if ((keep_bits[r >> 5] >> (r & 31)) & 1u) continue;
+      float* dst = img + static_cast<size_t>(r) * row + 4;
+      for (int c = lane; c < p.C; c += 32) dst[c] = 0.0f;
+    }
+  }
+}
+
 static size_t nms_smem_bytes(int P) {
   const size_t Pp = (static_cast<size_t>(P) + 15) & ~static_cast<size_t>(15);
   const size_t head = ((sizeof(NmsShared) + 15) & ~static_cast<size_t>(15)) + ((static_cast<size_t>((P + 31) / 32) * 4 + 15) & ~static_cast<size_t>(15));
@@ -458,19 +778,21 @@ struct NmsWorkspace {
   uint8_t* cand_cls;
   int32_t* order;
   int32_t* keep;
+  int32_t* large;
 };
 
 static size_t nms_ws_layout(int N, int P, void* ws, NmsWorkspace* out) {
   const size_t np = static_cast<size_t>(N) * P;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~static_cast<size_t>(255); return o; };
-  const size_t o_key = take(np * 4), o_ord = take(np * 4), o_keep = take(np * 4), o_cls = take(np);
+  const size_t o_key = take(np * 4), o_ord = take(np * 4), o_keep = take(np * 4), o_cls = take(np), o_large = take(static_cast<size_t>(N) * 4);
   if (out && ws) {
     unsigned char* b = static_cast<unsigned char*>(ws);
     out->cand_key = reinterpret_cast<float*>(b + o_key);
     out->order = reinterpret_cast<int32_t*>(b + o_ord);
     out->keep = reinterpret_cast<int32_t*>(b + o_keep);
     out->cand_cls = b + o_cls;
+    out->large = reinterpret_cast<int32_t*>(b + o_large);
   }
   return off;
 }
@@ -514,7 +836,22 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   p.score_thr = score_thr; p.top_k = top_k; p.per_class = per_class; p.scatter = fused ? 1 : 0;
   p.order = order ? order : w.order; p.order_cnt = order_cnt;
   p.keep = keep ? keep : w.keep; p.keep_cnt = keep_cnt;
-  nms_kernel<<<N, kNmsThreads, smem, st>>>(p);
+  p.trace = g_nms_trace;
+  // small-K images first (three per SM); whatever it flags as large goes through the tiled kernel (one per SM)
+  const size_t small_smem = ((sizeof(SmallShared) + 15) & ~static_cast<size_t>(15)) + (static_cast<size_t>((P + 31) / 32) * 4 + 16);
+  static bool cfg3 = false;
+  if (!cfg3) {
+    cudaError_t e = cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e)); return static_cast<int>(e); }
+    cfg3 = true;
+  }
+  if (small_smem <= 100 * 1024 && P <= kSmallWarps * 32 * kSmallRounds) {
+    nms_small_kernel<<<N, kSmallThreads, small_smem, st>>>(p, w.large);
+    if (int e = cuda_status(fn)) return e;
+    nms_kernel<<<N, kNmsThreads, smem, st>>>(p, w.large);
+  } else {
+    nms_kernel<<<N, kNmsThreads, smem, st>>>(p, nullptr);
+  }
   return cuda_status(fn);
 }
 
@@ -545,6 +882,8 @@ extern "C" int ssdh_iou(const float* t, int t_row_stride, int T, const float* s,
   iou_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(t, t_row_stride, T, s, s_row_stride, S, out, total);
   return cuda_status("ssdh_iou");
 }
+
+extern "C" __attribute__((visibility("default"))) void ssdh_debug_set_nms_trace(unsigned long long* buf) { g_nms_trace = buf; }
 
 extern "C" size_t ssdh_nms_workspace_bytes(int N, int P, int C) {
   (void)C;
