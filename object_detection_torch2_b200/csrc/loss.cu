@@ -31,6 +31,7 @@ constexpr int kMaxCluster = 8;
 constexpr int kMaxLossWarps = 32;
 constexpr int kListCap = 384;        // per-CTA candidates of the selected bucket
 constexpr int kGatherCap = 768;      // cluster-wide candidates finished locally
+constexpr int kCountCap = 384;       // up to here the order statistic is finished by direct counting
 // Two shapes of the same kernel (template parameters kT = threads per CTA, kCl = CTAs per cluster):
 //   <768, 4>: 4 CTAs x ~221 KB per image, one CTA per SM  -> every SM carries the same load (default when it fits)
 //   <384, 8>: 8 CTAs x ~110 KB per image                   -> larger images / more ground truth per image
@@ -118,6 +119,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// Same, with an L2 eviction policy: the head output is read exactly once, so its lines should be the first victims
+// (keeps the freshly written gradient -- which the backbone's backward reads next -- resident instead).
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
 }
 // Ampere-style async copies (LDGSTS): 16 bytes per lane, completion tracked per thread in commit groups.
@@ -327,19 +340,17 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   // ---- slab: every warp fetches its own dealt blocks (one per row slot) by TMA bulk copy onto its own mbarriers;
   // issued only now, after the ground truth landed, so the small loads were never queued behind this traffic ----
   if (p.bulk) {
-    if (lane == 0) {
-#pragma unroll
-      for (int s = 0; s < kSlots; ++s) mbar_init(&sh.mbar[s][warp], 1);
+    if (lane < kSlots) {                              // lane s initialises, arms and issues slot s: three copies in flight at once
+      const int s = lane;
+      mbar_init(&sh.mbar[s][warp], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-      for (int s = 0; s < kSlots; ++s) {
-        const int j = s * kSlotBlocks + warp;
-        if (j < my_blocks) {
-          const int gb = j * kCluster + rank;
-          const uint32_t bytes = static_cast<uint32_t>(min(kBlockRows, p.P - gb * kBlockRows)) * row * sizeof(float);
-          mbar_expect_tx(&sh.mbar[s][warp], bytes);
-          bulk_load(slab + static_cast<size_t>(j) * kBlockRows * row, img_in + static_cast<size_t>(gb) * kBlockRows * row, bytes, &sh.mbar[s][warp]);
-        }
+      const int j = s * kSlotBlocks + warp;
+      if (j < my_blocks) {
+        const int gb = j * kCluster + rank;
+        const uint32_t bytes = static_cast<uint32_t>(min(kBlockRows, p.P - gb * kBlockRows)) * row * sizeof(float);
+        mbar_expect_tx(&sh.mbar[s][warp], bytes);
+        bulk_load_hint(slab + static_cast<size_t>(j) * kBlockRows * row, img_in + static_cast<size_t>(gb) * kBlockRows * row, bytes,
+                       &sh.mbar[s][warp], policy_evict_first());
       }
     }
     __syncwarp();
@@ -607,6 +618,29 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       }
       __syncthreads();
       trace_point(p, 18);
+      if (total <= kCountCap) {
+        // few candidates (the usual case): exact order statistic by counting.  Thread i counts the candidates above
+        // its key and those equal to it; the (rem+1)-th largest is the key with  above <= rem < above + equal.
+        if (tid < total) {
+          const uint32_t mine = sh.gathered[tid];
+          int above = 0, equal = 0;
+          const uint4* g4 = reinterpret_cast<const uint4*>(sh.gathered);
+          const int n4 = total >> 2;
+          for (int i = 0; i < n4; ++i) {
+            const uint4 v = g4[i];
+            above += (v.x > mine) + (v.y > mine) + (v.z > mine) + (v.w > mine);
+            equal += (v.x == mine) + (v.y == mine) + (v.z == mine) + (v.w == mine);
+          }
+          for (int i = n4 << 2; i < total; ++i) {
+            const uint32_t v = sh.gathered[i];
+            above += v > mine;
+            equal += v == mine;
+          }
+          if (static_cast<uint32_t>(above) <= rem && rem < static_cast<uint32_t>(above + equal)) sh.sel_prefix = mine;
+        }
+        __syncthreads();
+        prefix = sh.sel_prefix;
+      } else {
       // Interior buckets pin the top 13 bits of the key: 19 bits remain -> 3 passes (8 + 8 + 3); the two clamped
       // end buckets span arbitrary keys -> 4 full passes.  One buffer per pass, one barrier per pass; every warp
       // resolves the bin redundantly from the same histogram.
@@ -628,6 +662,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
         __syncthreads();
         const int bin = find_bin_desc(lh, rem, lane);
         prefix |= static_cast<uint32_t>(bin) << shift;
+      }
       }
     } else {
       // fallback (a bucket with more than kGatherCap candidates, e.g. thousands of identical CEs):

@@ -151,6 +151,33 @@ candidate_kernel(const float* __restrict__ outputs, int C, size_t total_rows, fl
   }
 }
 
+// Branch-free pair test for the NMS inner loops.  Mirrors src/utils.py:74-77 followed by `> thr`:
+//   inter = clamp(w) * clamp(h);  value = inter > 0 ? inter / union : inter;  hit = value > thr.
+// e = inter - union * thr is a single FMA, so its sign is exact; when |e| clears the 2^-20 band the rounded
+// quotient is on the same side of thr with certainty.  Pairs inside the band (or with a degenerate union) report
+// `amb` and are settled by the caller with the IEEE division (iou_gt), which keeps keep-lists bit-identical.
+struct PairThr {
+  float thr, nthr, eps;
+  bool usable;
+};
+__host__ __device__ inline PairThr make_pair_thr(float thr) {
+  PairThr t;
+  t.thr = thr; t.nthr = -thr; t.eps = thr * 9.5367431640625e-07f;
+  t.usable = thr >= 1e-6f && thr <= 1e6f;
+  return t;
+}
+__device__ __forceinline__ bool pair_hit_fast(const float4 a, float a_area, const float4 b, float b_area, const PairThr& t, bool& amb) {
+  // boxes are (x1, x2, y1, y2)
+  const float w = fmaxf(fminf(a.y, b.y) - fmaxf(a.x, b.x), 0.0f);
+  const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.z, b.z), 0.0f);
+  const float inter = w * h;
+  const float uni = (a_area + b_area) - inter;
+  const float e = fmaf(uni, t.nthr, inter), m = uni * t.eps;
+  // inter == 0 gives e = -union * thr < -m for any sane union; a non-positive / non-finite union lands in the band
+  amb = !(fabsf(e) > m) || !(uni >= 1e-30f);
+  return e > m;
+}
+
 // ------------------------------------------------------------------------------------------------
 // NMS kernel: one CTA per image
 // ------------------------------------------------------------------------------------------------
@@ -338,7 +365,20 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
 
   // ---- C. greedy suppression -----------------------------------------------------------------------------
   const ThrBand band = p.band;
+  const PairThr pt = make_pair_thr(band.thr);
   const int limit = p.top_k > 0 ? p.top_k : 0x7fffffff;
+  // pair test: fast band decision, the (rare) borderline pair is settled with the IEEE division
+  auto suppresses = [&](const float4 kb, float ka, const float4 mb, float ma) -> bool {
+    bool amb;
+    bool hit = pair_hit_fast(kb, ka, mb, ma, pt, amb);
+    if (amb || !pt.usable) {
+      Corners o, m;
+      o.x1 = kb.x; o.x2 = kb.y; o.y1 = kb.z; o.y2 = kb.w; o.area = ka;
+      m.x1 = mb.x; m.x2 = mb.y; m.y1 = mb.z; m.y2 = mb.w; m.area = ma;
+      hit = iou_gt(o, m, band);
+    }
+    return hit;
+  };
   for (int base = 0; base < K; base += kNmsThreads) {
     if (sh.stop) break;
     const int i = base + tid;
@@ -351,16 +391,14 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       me = make_corners(b[0], b[1], b[2], b[3]);
       if (p.per_class) my_cls = cls_in[my_row];
     }
+    const float4 me4 = make_float4(me.x1, me.x2, me.y1, me.y2);
     const int kept_before = sh.kept;
     // (1) against everything kept by earlier tiles: broadcast reads of the kept list
     for (int j0 = 0; j0 < kept_before; j0 += 32) {
       if (!__any_sync(0xffffffffu, alive)) break;
       const int j1 = min(j0 + 32, kept_before);
       for (int j = j0; j < j1; ++j) {
-        const float4 kb = k_box[j];
-        Corners o;
-        o.x1 = kb.x; o.x2 = kb.y; o.y1 = kb.z; o.y2 = kb.w; o.area = k_area[j];
-        bool hit = iou_gt(o, me, band);
+        bool hit = suppresses(k_box[j], k_area[j], me4, me.area);
         if (p.per_class) hit = hit && (k_cls[j] == my_cls);
         alive = alive && !hit;
       }
@@ -377,10 +415,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       if (warp == w) {
         const int kept_now = sh.kept;
         for (int j = kept_before; j < kept_now; ++j) {            // boxes kept by earlier warps of this tile
-          const float4 kb = k_box[j];
-          Corners o;
-          o.x1 = kb.x; o.x2 = kb.y; o.y1 = kb.z; o.y2 = kb.w; o.area = k_area[j];
-          bool hit = iou_gt(o, me, band);
+          bool hit = suppresses(k_box[j], k_area[j], me4, me.area);
           if (p.per_class) hit = hit && (k_cls[j] == my_cls);
           alive = alive && !hit;
         }
@@ -397,7 +432,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
           o.area = __shfl_sync(0xffffffffu, me.area, j);
           const int ocls = __shfl_sync(0xffffffffu, my_cls, j);
           if (alive && lane > j) {
-            bool hit = iou_gt(o, me, band);
+            bool hit = suppresses(make_float4(o.x1, o.x2, o.y1, o.y2), o.area, me4, me.area);
             if (p.per_class) hit = hit && (ocls == my_cls);
             alive = !hit;
           }
@@ -445,33 +480,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
   }
 }
 
-
-// Branch-free pair test for the NMS inner loops.  Mirrors src/utils.py:74-77 followed by `> thr`:
-//   inter = clamp(w) * clamp(h);  value = inter > 0 ? inter / union : inter;  hit = value > thr.
-// e = inter - union * thr is a single FMA, so its sign is exact; when |e| clears the 2^-20 band the rounded
-// quotient is on the same side of thr with certainty.  Pairs inside the band (or with a degenerate union) report
-// `amb` and are settled by the caller with the IEEE division (iou_gt), which keeps keep-lists bit-identical.
-struct PairThr {
-  float thr, nthr, eps;
-  bool usable;
-};
-__host__ __device__ inline PairThr make_pair_thr(float thr) {
-  PairThr t;
-  t.thr = thr; t.nthr = -thr; t.eps = thr * 9.5367431640625e-07f;
-  t.usable = thr >= 1e-6f && thr <= 1e6f;
-  return t;
-}
-__device__ __forceinline__ bool pair_hit_fast(const float4 a, float a_area, const float4 b, float b_area, const PairThr& t, bool& amb) {
-  // boxes are (x1, x2, y1, y2)
-  const float w = fmaxf(fminf(a.y, b.y) - fmaxf(a.x, b.x), 0.0f);
-  const float h = fmaxf(fminf(a.w, b.w) - fmaxf(a.z, b.z), 0.0f);
-  const float inter = w * h;
-  const float uni = (a_area + b_area) - inter;
-  const float e = fmaf(uni, t.nthr, inter), m = uni * t.eps;
-  // inter == 0 gives e = -union * thr < -m for any sane union; a non-positive / non-finite union lands in the band
-  amb = !(fabsf(e) > m) || !(uni >= 1e-30f);
-  return e > m;
-}
 
 // ------------------------------------------------------------------------------------------------
 // NMS, small-K kernel: images with at most kSmallCap candidates (every realistic, trained-like image).
