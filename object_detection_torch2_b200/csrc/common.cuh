@@ -21,6 +21,8 @@ constexpr int kMaxClasses = 64;
 
 void set_error(const char* fmt, ...);
 int cuda_status(const char* what);   // cudaGetLastError -> return code (0 or cudaError_t), sets message
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (kernel, device): set it once for each pair.  0 = OK.
+int ensure_dyn_smem(const void* kernel, int bytes, const char* what);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

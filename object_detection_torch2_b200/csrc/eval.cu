@@ -159,12 +159,7 @@ extern "C" int ssdh_eval_accumulate(const float* outputs, const float* gts, int 
   if (!ws || ws_bytes < ssdh_eval_workspace_bytes(N, P, C, G)) { set_error("ssdh_eval_accumulate: workspace too small"); return SSDH_E_WORKSPACE; }
   const size_t smem = eval_smem_bytes(P, C, G);
   if (smem > 227 * 1024) { set_error("ssdh_eval_accumulate: needs %zu bytes of shared memory", smem); return SSDH_E_LIMIT; }
-  static bool cfg = false;
-  if (!cfg) {
-    cudaError_t e = cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_error("ssdh_eval_accumulate: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
-    cfg = true;
-  }
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(eval_kernel), 227 * 1024, "ssdh_eval_accumulate")) return e;
   EvalParams p;
   p.outputs = outputs; p.gts = gts; p.P = P; p.C = C; p.G = G;
   p.band = make_band(iou_thr);

@@ -886,12 +886,7 @@ static bool pick_shape(int P, int C, int G, LossShape* out) {
 
 template <int kC, int kT, int kCl>
 static int launch_loss(const LossParams& p, size_t smem, cudaStream_t st) {
-  static bool configured = false;     // per instantiation; one process drives one device
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(multibox_loss_kernel<kC, kT, kCl>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
-    if (e != cudaSuccess) { set_error("ssdh_multibox_loss: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
-    configured = true;
-  }
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<kC, kT, kCl>), static_cast<int>(kMaxDynSmem), "ssdh_multibox_loss")) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(p.N) * kCl);
   cfg.blockDim = dim3(kT);
@@ -990,10 +985,10 @@ extern "C" int ssdh_device_info(int* sm_count, int* max_smem_optin, int* loss_cl
     cfg.attrs = attr; cfg.numAttrs = 1;
     int nc = 0;
     if (shape.cluster == 4) {
-      cudaFuncSetAttribute(multibox_loss_kernel<21, 768, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
+      ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<21, 768, 4>), static_cast<int>(kMaxDynSmem), "ssdh_device_info");
       e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 768, 4>, &cfg);
     } else {
-      cudaFuncSetAttribute(multibox_loss_kernel<21, 384, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
+      ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<21, 384, 8>), static_cast<int>(kMaxDynSmem), "ssdh_device_info");
       e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 384, 8>, &cfg);
     }
     if (e != cudaSuccess) { set_error("ssdh_device_info: occupancy: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }

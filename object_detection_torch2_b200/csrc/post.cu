@@ -821,8 +821,7 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   if (fused) {
     const unsigned blocks = static_cast<unsigned>((total_rows + kTileRows - 1) / kTileRows);
     const size_t tile_bytes = static_cast<size_t>(kTileRows) * row * sizeof(float);
-    static bool cfg = false;
-    if (!cfg) { cudaFuncSetAttribute(decode_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; }
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_score_kernel), 96 * 1024, fn)) return e;
     const int vec_ok = aligned16(outputs) && ((static_cast<size_t>(kTileRows) * row) % 4 == 0);
     decode_score_kernel<<<blocks, kTileRows, tile_bytes, st>>>(outputs, reinterpret_cast<const float4*>(priors), P, C, total_rows,
                                                               w.cand_key, w.cand_cls, vec_ok);
@@ -831,12 +830,7 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
     candidate_kernel<<<blocks, 256, 0, st>>>(outputs, C, total_rows, w.cand_key, w.cand_cls);
   }
   if (int e = cuda_status(fn)) return e;
-  static bool cfg2 = false;
-  if (!cfg2) {
-    cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e)); return static_cast<int>(e); }
-    cfg2 = true;
-  }
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel), 227 * 1024, fn)) return e;
   NmsParams p;
   p.outputs = outputs; p.P = P; p.C = C;
   p.cand_key = w.cand_key; p.cand_cls = w.cand_cls;
@@ -847,12 +841,7 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   p.trace = g_nms_trace;
   // small-K images first (three per SM); whatever it flags as large goes through the tiled kernel (one per SM)
   const size_t small_smem = ((sizeof(SmallShared) + 15) & ~static_cast<size_t>(15)) + (static_cast<size_t>((P + 31) / 32) * 4 + 16);
-  static bool cfg3 = false;
-  if (!cfg3) {
-    cudaError_t e = cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", fn, cudaGetErrorString(e)); return static_cast<int>(e); }
-    cfg3 = true;
-  }
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel), 100 * 1024, fn)) return e;
   if (small_smem <= 100 * 1024 && P <= kSmallWarps * 32 * kSmallRounds) {
     nms_small_kernel<<<N, kSmallThreads, small_smem, st>>>(p, w.large);
     if (int e = cuda_status(fn)) return e;

@@ -1,6 +1,10 @@
 // Error plumbing and build/device facts of libssdhead.
 #include <stdarg.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace ssdh {
@@ -19,6 +23,22 @@ int cuda_status(const char* what) {
   if (e == cudaSuccess) return 0;
   set_error("%s: %s", what, cudaGetErrorString(e));
   return static_cast<int>(e);
+}
+
+int ensure_dyn_smem(const void* kernel, int bytes, const char* what) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("%s: cudaGetDevice: %s", what, cudaGetErrorString(e)); return static_cast<int>(e); }
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(kernel, dev);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return 0;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(%d bytes): %s", what, bytes, cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
+  done[key] = bytes;
+  return 0;
 }
 
 }  // namespace ssdh

@@ -276,3 +276,40 @@ def test_sharded_loss_equals_whole_batch(priors_gpu):
         grads.append(g)
     torch.testing.assert_close(parts[0] + parts[1], whole, rtol=1e-6, atol=0)
     assert torch.equal(torch.cat(grads), gw)
+
+
+@pytest.mark.parametrize("g_rows", [42, 64])
+def test_loss_many_ground_truth_rows(g_rows, priors_cpu, priors_gpu):
+    # VOC images carry up to 42 boxes; G > 32 exercises the high mask word, large G the 8-CTA kernel shape
+    t = synth.make_targets(2, 140 + g_rows, max_boxes=g_rows, min_boxes=g_rows)
+    assert t.shape[1] == g_rows
+    t[:, :, 2:4] *= 0.4                      # smaller boxes keep the image out of the crowded regime for one of them
+    o = synth.make_outputs(2, 141, "D2")
+    run_and_compare(o, t, priors_cpu, priors_gpu)
+    assert torch.equal(ops.match(t.to(DEV), priors_gpu).mask.cpu(), head.match_mask(t, priors_cpu))
+
+
+def test_loss_full_size_properties(priors_gpu):
+    # config 4 of BASELINE.json per-GPU width (128 images): size-independent properties instead of the slow oracle
+    N = 128
+    o, t = synth.make_batch(N, 151, "D2")
+    od, td = o.to(DEV), t.to(DEV)
+    loss, grad, stats = ops.multibox_loss_raw(od, td, priors_gpu, want_stats=True)
+    st = ops.stats_to_numpy(stats)
+    # batch mean == mean of the per-image losses; images are independent (a sub-batch gives the same per-image numbers)
+    np.testing.assert_allclose(float(loss), st["loss"].astype(np.float64).mean(), rtol=1e-6)
+    sub = slice(40, 48)
+    l2, g2, s2 = ops.multibox_loss_raw(od[sub].contiguous(), td[sub].contiguous(), priors_gpu, n_global=N, want_stats=True)
+    st2 = ops.stats_to_numpy(s2)
+    assert np.array_equal(st2["loss"], st["loss"][sub]) and np.array_equal(st2["pos_raw"], st["pos_raw"][sub])
+    assert torch.equal(g2, grad[sub])
+    # split arithmetic, selection counts and gradient support
+    pos, kp, kn = st["pos_raw"].astype(np.int64), st["k_pos"], st["k_neg"]
+    crowded = pos * 3 > 8732 - pos
+    assert np.array_equal(kp, np.where(crowded, (8732 - pos) // 3, pos)) and np.array_equal(kn, np.where(crowded, 8732 - pos, pos * 3))
+    assert (st["pos_sel"] <= kp).all() and (st["neg_sel"] <= kn).all()
+    nonzero_rows = (grad.abs().sum(dim=2) > 0).sum(dim=1).cpu().numpy()
+    assert (nonzero_rows <= st["pos_sel"] + st["neg_sel"]).all() and (nonzero_rows >= st["pos_sel"] + st["neg_sel"] - 2).all()
+    # every selected row's class gradient sums to ~0 for negatives (softmax - e0) -- spot check via the void column sign
+    assert float(grad[:, :, 4:].sum(dim=2).abs().max()) < 1e-3
+    assert torch.isfinite(grad).all() and torch.isfinite(loss)
