@@ -179,8 +179,10 @@ def main():
     losses = torch.zeros(ROT, dtype=torch.float32, device=dev)
 
     def step(i):
+        # software pipelining: while batch i is on chip the kernel asks the L2 for batch i+1 (HBM is idle then)
+        nxt = (i + 1) % ROT
         ops.multibox_loss_raw(outs[i], tgts[i], priors, a=1.0, threshold=0.25, n_global=n_global, want_grad=True,
-                              loss_out=losses[i], grad_out=grads[i])
+                              loss_out=losses[i], grad_out=grads[i], next_outputs=outs[nxt], next_targets=tgts[nxt])
 
     # one CUDA graph = ROT consecutive steps (one per rotating buffer pair)
     cap = torch.cuda.Stream(device=dev)
@@ -293,7 +295,7 @@ def main():
             "config": {"workload": "SSD300 head training step: IoU match + MultiBox loss fwd+grad, batch 32 per GPU, G<=20, dist " + args.dist,
                        "global_batch": n_global, "priors": P, "classes": C, "gt_rows": G,
                        "l2": f"inputs larger than L2: rotation over {ROT} (outputs, grad) buffer pairs = {ROT * 2 * BATCH * SLAB / 1e6:.0f} MB",
-                       "launch": f"CUDA graph of {ROT} steps, C ABI ssdh_multibox_loss", "parallelism": f"dp{world} (images sharded, scalar all-reduce per replay)"},
+                       "launch": f"CUDA graph of {ROT} steps, C ABI ssdh_multibox_loss_pipelined (in-kernel L2 prefetch of the next batch, programmatic dependent launch between steps)", "parallelism": f"dp{world} (images sharded, scalar all-reduce per replay)"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": steps, "clocks": clocks, "loss": loss_value}
 
     if rank == 0 and world == 1 and not args.no_extras:

@@ -107,6 +107,18 @@ SSDH_API int ssdh_multibox_loss(const float* outputs, const float* targets, cons
                        float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
                        void* ws, size_t ws_bytes, ssdh_stream_t stream);
 
+/* Same as ssdh_multibox_loss, plus software pipelining across micro-batches: once this batch's slabs are on chip (HBM is
+ * then idle until the gradient is written) every CTA asks the L2 for the blocks it will read from next_outputs /
+ * next_targets (same shapes; either may be NULL) in the NEXT call.  Pure hint: no data is changed. */
+SSDH_API int ssdh_multibox_loss_pipelined(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
+                       float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
+                       void* ws, size_t ws_bytes, ssdh_stream_t stream, const float* next_outputs, const float* next_targets);
+
+/* Software pipelining hook: pull [ptr, ptr + bytes) from HBM into the L2 (cp.async.bulk.prefetch.L2), e.g. the NEXT
+ * micro-batch's head output on a side stream while ssdh_multibox_loss works on the current one.  Reads nothing into
+ * the SMs, changes no data; ptr must be 16-byte aligned. */
+SSDH_API int ssdh_prefetch_l2(const void* ptr, size_t bytes, ssdh_stream_t stream);
+
 /* grad *= *scale (device scalar), skipped entirely when *scale == 1: the autograd chain-rule hook. */
 SSDH_API int ssdh_scale_inplace(float* x, size_t n, const float* scale, ssdh_stream_t stream);
 

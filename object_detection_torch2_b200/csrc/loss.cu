@@ -40,6 +40,8 @@ struct LossParams {
   const float* outputs;
   const float* targets;
   const float4* priors;
+  const float* next_outputs;   // optional: the next micro-batch (same shape), prefetched into L2 once this one is on chip
+  const float* next_targets;
   int N, P, C, G;
   float a;
   ThrBand band;
@@ -271,6 +273,11 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   LossShared& sh = *reinterpret_cast<LossShared*>(smem_raw + slab_bytes + ((static_cast<size_t>(G) * sizeof(GtRec) + 15) & ~static_cast<size_t>(15)));
 
   const float* img_in = p.outputs + static_cast<size_t>(n) * p.P * row;
+
+  // Programmatic dependent launch: let the NEXT grid in the stream be scheduled as soon as SMs free up.  It may run
+  // everything that only reads its own inputs (load, match, CE, selection) under this grid's tail; it blocks at
+  // griddepcontrol.wait below, before its first global write (workspace, loss, stats, gradient).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // ---- setup ------------------------------------------------------------------------------------
   trace_point(p, 0);
@@ -533,6 +540,23 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     if (lane == 0 && c) atomicAdd(&sh.pos_local, c);
   }
 
+  // ---- software pipelining across micro-batches: HBM goes quiet from here until the gradient leaves, so every
+  // warp now asks the L2 for the same blocks of the NEXT batch (this SM will read them again in the next launch) ------
+  if (p.next_outputs != nullptr && p.bulk && lane < kSlots) {
+    const int j = lane * kSlotBlocks + warp;
+    if (j < my_blocks) {
+      const int gb = j * kCluster + rank;
+      const uint32_t bytes = static_cast<uint32_t>(min(kBlockRows, p.P - gb * kBlockRows)) * row * sizeof(float);
+      const float* nsrc = p.next_outputs + static_cast<size_t>(n) * p.P * row + static_cast<size_t>(gb) * kBlockRows * row;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc), "r"(bytes) : "memory");
+    }
+  }
+  if (p.next_targets != nullptr && rank == 0 && tid == 32 && G > 0) {
+    const uint32_t bytes = (static_cast<uint32_t>(G) * row * sizeof(float)) & ~15u;
+    const float* nt = p.next_targets + static_cast<size_t>(n) * G * row;
+    if (bytes && (reinterpret_cast<uintptr_t>(nt) & 15u) == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nt), "r"(bytes) : "memory");
+  }
+
   // ---- cluster exchange #1: positives + bucket histograms of both sets -----------------------------------------
   trace_point(p, 5);
   cluster.sync();
@@ -738,6 +762,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   }
 
   // ---- cluster exchange #2: per-image loss, stats, batch mean ----------------------------------------------------
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous grid (same workspace, maybe same outputs) is complete
   cluster.sync();          // last use of distributed shared memory: CTAs are independent from here on
   trace_point(p, 9);
   if (rank == 0 && tid == 0) {
@@ -892,13 +917,16 @@ static int launch_loss(const LossParams& p, size_t smem, cudaStream_t st) {
   cfg.blockDim = dim3(kT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static const int pdl = [] { const char* e = getenv("SSDH_LOSS_PDL"); return e ? atoi(e) : 1; }();
+  cfg.numAttrs = pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, multibox_loss_kernel<kC, kT, kCl>, p);
   if (e != cudaSuccess) { set_error("ssdh_multibox_loss: launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
   return 0;
@@ -919,9 +947,9 @@ extern "C" size_t ssdh_multibox_loss_workspace_bytes(int N, int P, int C, int G)
   return 16 + static_cast<size_t>(N > 0 ? N : 0) * sizeof(double);
 }
 
-extern "C" int ssdh_multibox_loss(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
-                                  float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
-                                  void* ws, size_t ws_bytes, ssdh_stream_t stream) {
+static int multibox_loss_impl(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
+                              float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
+                              void* ws, size_t ws_bytes, ssdh_stream_t stream, const float* next_outputs, const float* next_targets) {
   if (!outputs || !priors || !loss || N <= 0 || P <= 0 || C <= 0 || G < 0 || n_global <= 0 || (G > 0 && !targets)) {
     set_error("ssdh_multibox_loss: NULL pointer or non-positive dimension");
     return SSDH_E_ARG;
@@ -942,6 +970,8 @@ extern "C" int ssdh_multibox_loss(const float* outputs, const float* targets, co
 
   LossParams p;
   p.outputs = outputs; p.targets = targets; p.priors = reinterpret_cast<const float4*>(priors);
+  p.next_outputs = (next_outputs && aligned16(next_outputs)) ? next_outputs : nullptr;
+  p.next_targets = next_targets;
   p.N = N; p.P = P; p.C = C; p.G = G;
   p.a = a; p.band = make_band(thr);
   p.inv_n_global = 1.0f / static_cast<float>(n_global);
@@ -957,6 +987,19 @@ extern "C" int ssdh_multibox_loss(const float* outputs, const float* targets, co
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (C == 21) return launch_loss_shape<21>(p, shape, st);
   return launch_loss_shape<0>(p, shape, st);
+}
+
+extern "C" int ssdh_multibox_loss(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
+                                  float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
+                                  void* ws, size_t ws_bytes, ssdh_stream_t stream) {
+  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, nullptr, nullptr);
+}
+
+extern "C" int ssdh_multibox_loss_pipelined(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
+                                            float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
+                                            void* ws, size_t ws_bytes, ssdh_stream_t stream, const float* next_outputs,
+                                            const float* next_targets) {
+  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, next_outputs, next_targets);
 }
 
 // Debug hook (not part of the public header): device buffer of [N * 8][16] u64 phase stamps, or NULL to disable.

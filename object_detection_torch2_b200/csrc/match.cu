@@ -228,6 +228,16 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, size_
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= s;
 }
 
+// L2 prefetch: one thread per 8 KB chunk, a handful of CTAs -- leaves the SMs to whatever else is running.
+constexpr size_t kPrefetchChunk = 8192;
+__global__ void __launch_bounds__(128) prefetch_l2_kernel(const unsigned char* __restrict__ ptr, size_t bytes) {
+  const size_t chunk = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t off = chunk * kPrefetchChunk;
+  if (off >= bytes) return;
+  const unsigned int n = static_cast<unsigned int>(bytes - off < kPrefetchChunk ? ((bytes - off) & ~static_cast<size_t>(15)) : kPrefetchChunk);
+  if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + off), "r"(n) : "memory");
+}
+
 static int check_gt(const char* fn, int N, int G) {
   if (N <= 0 || G < 0) { set_error("%s: bad N=%d G=%d", fn, N, G); return SSDH_E_ARG; }
   if (G > kMaxGT) { set_error("%s: G=%d exceeds the limit of %d ground-truth rows per image", fn, G, kMaxGT); return SSDH_E_LIMIT; }
@@ -299,6 +309,15 @@ extern "C" int ssdh_kplus1_value(const float* values, int rows, int len, const i
   if (!values || !k || !out || rows <= 0 || len <= 0) { set_error("ssdh_kplus1_value: bad argument"); return SSDH_E_ARG; }
   kplus1_kernel<<<rows, 512, 0, static_cast<cudaStream_t>(stream)>>>(values, len, k, out);
   return cuda_status("ssdh_kplus1_value");
+}
+
+extern "C" int ssdh_prefetch_l2(const void* ptr, size_t bytes, ssdh_stream_t stream) {
+  if (!ptr) { set_error("ssdh_prefetch_l2: NULL"); return SSDH_E_ARG; }
+  if (!aligned16(ptr)) { set_error("ssdh_prefetch_l2: ptr must be 16-byte aligned"); return SSDH_E_ALIGN; }
+  if (bytes < 16) return 0;
+  const size_t chunks = (bytes + kPrefetchChunk - 1) / kPrefetchChunk;
+  prefetch_l2_kernel<<<static_cast<unsigned>((chunks + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned char*>(ptr), bytes);
+  return cuda_status("ssdh_prefetch_l2");
 }
 
 extern "C" int ssdh_scale_inplace(float* x, size_t n, const float* scale, ssdh_stream_t stream) {

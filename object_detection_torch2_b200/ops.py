@@ -180,7 +180,8 @@ assert STATS_DTYPE.itemsize == ctypes.sizeof(ImageStats)
 def multibox_loss_raw(outputs: torch.Tensor, targets: torch.Tensor, priors: torch.Tensor, a: float = 1.0, threshold: float = 0.25,
                       n_global: Optional[int] = None, want_grad: bool = True, want_stats: bool = False,
                       loss_out: Optional[torch.Tensor] = None, grad_out: Optional[torch.Tensor] = None,
-                      stats_out: Optional[torch.Tensor] = None):
+                      stats_out: Optional[torch.Tensor] = None, next_outputs: Optional[torch.Tensor] = None,
+                      next_targets: Optional[torch.Tensor] = None):
     """One launch: loss (0-d), d loss / d outputs (or None) and per-image stats (uint8 (N, 32) view of ssdh_image_stats, or None).
 
     Inputs must already be contiguous fp32 CUDA tensors (this is the graph-capturable hot call)."""
@@ -199,10 +200,17 @@ def multibox_loss_raw(outputs: torch.Tensor, targets: torch.Tensor, priors: torc
     with torch.cuda.device(dev):
         nbytes = lib.ssdh_multibox_loss_workspace_bytes(N, P, C, G)
         ws = _workspace("loss", nbytes, dev, zero=True)
-        check(lib.ssdh_multibox_loss(outputs.data_ptr(), targets.data_ptr() if G > 0 else None, priors.data_ptr(), N, P, C, G,
-                                     float(a), float(threshold), int(n_global or N), loss_out.data_ptr(),
-                                     _ptr(grad_out) if want_grad else None, _ptr(stats_out) if want_stats else None,
-                                     ws.data_ptr(), ws.numel(), _stream()), "ssdh_multibox_loss")
+        args = (outputs.data_ptr(), targets.data_ptr() if G > 0 else None, priors.data_ptr(), N, P, C, G,
+                float(a), float(threshold), int(n_global or N), loss_out.data_ptr(),
+                _ptr(grad_out) if want_grad else None, _ptr(stats_out) if want_stats else None,
+                ws.data_ptr(), ws.numel(), _stream())
+        if next_outputs is None and next_targets is None:
+            check(lib.ssdh_multibox_loss(*args), "ssdh_multibox_loss")
+        else:                                   # L2 prefetch of the next micro-batch (same shapes) from inside the kernel
+            _need_cuda(next_outputs, next_targets)
+            if next_outputs is not None and next_outputs.shape != outputs.shape:
+                raise ValueError("next_outputs must have the shape of outputs")
+            check(lib.ssdh_multibox_loss_pipelined(*args, _ptr(next_outputs), _ptr(next_targets)), "ssdh_multibox_loss_pipelined")
     return loss_out, (grad_out if want_grad else None), (stats_out if want_stats else None)
 
 
@@ -238,6 +246,15 @@ def multibox_loss(outputs: torch.Tensor, targets: torch.Tensor, priors: torch.Te
     _need_cuda(outputs, targets, priors)
     o = outputs if (outputs.dtype == torch.float32 and outputs.is_contiguous()) else outputs.float().contiguous()
     return _MultiBoxLossFn.apply(o, _f32c(targets.detach()), _f32c(priors.detach()), float(a), float(threshold), n_global)
+
+
+def prefetch_l2(t: torch.Tensor) -> None:
+    """Pull a tensor from HBM into L2 on the current stream (software pipelining of the next micro-batch)."""
+    lib = _lib.load()
+    _need_cuda(t)
+    if t.numel():
+        with torch.cuda.device(t.device):
+            check(lib.ssdh_prefetch_l2(t.data_ptr(), t.numel() * t.element_size(), _stream()), "ssdh_prefetch_l2")
 
 
 # ------------------------------------------------------------------------------------------------ I1-I4
