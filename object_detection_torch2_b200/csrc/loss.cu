@@ -31,7 +31,6 @@ constexpr int kMaxCluster = 8;
 constexpr int kMaxLossWarps = 32;
 constexpr int kListCap = 384;        // per-CTA candidates of the selected bucket
 constexpr int kGatherCap = 768;      // cluster-wide candidates finished locally
-constexpr int kCountCap = 384;       // up to here the order statistic is finished by direct counting
 // Two shapes of the same kernel (template parameters kT = threads per CTA, kCl = CTAs per cluster):
 //   <768, 4>: 4 CTAs x ~221 KB per image, one CTA per SM  -> every SM carries the same load (default when it fits)
 //   <384, 8>: 8 CTAs x ~110 KB per image                   -> larger images / more ground truth per image
@@ -642,25 +641,31 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       }
       __syncthreads();
       trace_point(p, 18);
-      if (total <= kCountCap) {
-        // few candidates (the usual case): exact order statistic by counting.  Thread i counts the candidates above
-        // its key and those equal to it; the (rem+1)-th largest is the key with  above <= rem < above + equal.
-        if (tid < total) {
-          const uint32_t mine = sh.gathered[tid];
+      if (total <= 256) {
+        // few candidates (the usual case): exact order statistic by counting, spread over the whole CTA.  Thread t
+        // compares candidate t % 256 with one third of the list and adds its partial counts; the (rem+1)-th largest
+        // is the key with  above <= rem < above + equal.  tot[] / hist[1][] are zero here (see above).
+        uint32_t* cnt_above = &sh.tot[0][0];
+        uint32_t* cnt_equal = &sh.hist[1][0][0];
+        constexpr int kParts = kLossThreads / 256;                 // 3 with 768 threads, 1 with 384
+        const int ci = tid & 255, part = tid >> 8;
+        if (ci < total && part < kParts) {
+          const uint32_t mine = sh.gathered[ci];
+          const int per = (total + kParts - 1) / kParts;
+          const int j0 = part * per, j1 = min(total, j0 + per);
           int above = 0, equal = 0;
-          const uint4* g4 = reinterpret_cast<const uint4*>(sh.gathered);
-          const int n4 = total >> 2;
-          for (int i = 0; i < n4; ++i) {
-            const uint4 v = g4[i];
-            above += (v.x > mine) + (v.y > mine) + (v.z > mine) + (v.w > mine);
-            equal += (v.x == mine) + (v.y == mine) + (v.z == mine) + (v.w == mine);
-          }
-          for (int i = n4 << 2; i < total; ++i) {
-            const uint32_t v = sh.gathered[i];
+          for (int j = j0; j < j1; ++j) {
+            const uint32_t v = sh.gathered[j];
             above += v > mine;
             equal += v == mine;
           }
-          if (static_cast<uint32_t>(above) <= rem && rem < static_cast<uint32_t>(above + equal)) sh.sel_prefix = mine;
+          if (above) atomicAdd(&cnt_above[ci], static_cast<uint32_t>(above));
+          if (equal) atomicAdd(&cnt_equal[ci], static_cast<uint32_t>(equal));
+        }
+        __syncthreads();
+        if (tid < total) {
+          const uint32_t above = cnt_above[tid], equal = cnt_equal[tid];
+          if (above <= rem && rem < above + equal) sh.sel_prefix = sh.gathered[tid];
         }
         __syncthreads();
         prefix = sh.sel_prefix;
