@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kTileRows)
 decode_score_kernel(float* __restrict__ outputs, const float4* __restrict__ priors, int P, int C, size_t total_rows,
                     float* __restrict__ cand_key, uint8_t* __restrict__ cand_cls, int vec_ok) {
   extern __shared__ __align__(16) float tile[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // let the NMS grid get scheduled early (it waits below)
   const int row = 4 + C;
   const size_t r0 = static_cast<size_t>(blockIdx.x) * kTileRows;
   const int rows = static_cast<int>(min(static_cast<size_t>(kTileRows), total_rows - r0));
@@ -211,6 +212,7 @@ struct NmsShared {
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, const int32_t* __restrict__ large) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = blockIdx.x, P = p.P, row = 4 + p.C;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (large != nullptr && large[n] == 0) return;          // already handled by nms_small_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -527,6 +529,8 @@ __global__ void __launch_bounds__(kSmallThreads, 3) nms_small_kernel(const NmsPa
   int32_t* keep = p.keep + static_cast<size_t>(n) * P;
   float* img = p.outputs + static_cast<size_t>(n) * P * row;
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");                  // candidate keys / decoded boxes of the previous grid are complete
   NMS_TRACE(0);
   // ---- A. candidates in row order: warp w owns a contiguous chunk of rows; all of a lane's loads are issued before
   // the first ballot so the chunk costs one memory latency, not one per 32 rows -----------------------------------------
@@ -842,14 +846,28 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   // small-K images first (three per SM); whatever it flags as large goes through the tiled kernel (one per SM)
   const size_t small_smem = ((sizeof(SmallShared) + 15) & ~static_cast<size_t>(15)) + (static_cast<size_t>((P + 31) / 32) * 4 + 16);
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel), 100 * 1024, fn)) return e;
+  // Programmatic dependent launch: each grid may be scheduled while its predecessor drains and blocks in
+  // griddepcontrol.wait before touching the predecessor's results -- hides the launch latency between the kernels.
+  auto launch_pdl = [&](auto kernel, int threads, size_t dyn_smem, auto... args) -> int {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(N));
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = dyn_smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e != cudaSuccess) { set_error("%s: launch: %s", fn, cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
+    return 0;
+  };
   if (small_smem <= 100 * 1024 && P <= kSmallWarps * 32 * kSmallRounds) {
-    nms_small_kernel<<<N, kSmallThreads, small_smem, st>>>(p, w.large);
-    if (int e = cuda_status(fn)) return e;
-    nms_kernel<<<N, kNmsThreads, smem, st>>>(p, w.large);
-  } else {
-    nms_kernel<<<N, kNmsThreads, smem, st>>>(p, nullptr);
+    if (int e = launch_pdl(nms_small_kernel, kSmallThreads, small_smem, p, w.large)) return e;
+    return launch_pdl(nms_kernel, kNmsThreads, smem, p, static_cast<const int32_t*>(w.large));
   }
-  return cuda_status(fn);
+  return launch_pdl(nms_kernel, kNmsThreads, smem, p, static_cast<const int32_t*>(nullptr));
 }
 
 }  // namespace ssdh
