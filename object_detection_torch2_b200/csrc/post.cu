@@ -126,6 +126,7 @@ decode_score_kernel(float* __restrict__ outputs, const float4* __restrict__ prio
 __global__ void __launch_bounds__(256)
 candidate_kernel(const float* __restrict__ outputs, int C, size_t total_rows, float* __restrict__ cand_key,
                  uint8_t* __restrict__ cand_cls) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int row = 4 + C;
   const int lane = threadIdx.x & 31;
   const size_t warp_global = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -820,21 +821,10 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   if (!aligned16(ws) || (fused && !aligned16(priors))) { set_error("%s: ws/priors must be 16-byte aligned", fn); return SSDH_E_ALIGN; }
   NmsWorkspace w;
   nms_ws_layout(N, P, ws, &w);
-  const size_t total_rows = static_cast<size_t>(N) * P;
   const int row = 4 + C;
-  if (fused) {
-    const unsigned blocks = static_cast<unsigned>((total_rows + kTileRows - 1) / kTileRows);
-    const size_t tile_bytes = static_cast<size_t>(kTileRows) * row * sizeof(float);
-    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_score_kernel), 96 * 1024, fn)) return e;
-    const int vec_ok = aligned16(outputs) && ((static_cast<size_t>(kTileRows) * row) % 4 == 0);
-    decode_score_kernel<<<blocks, kTileRows, tile_bytes, st>>>(outputs, reinterpret_cast<const float4*>(priors), P, C, total_rows,
-                                                              w.cand_key, w.cand_cls, vec_ok);
-  } else {
-    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((total_rows + 7) / 8, 148 * 16));
-    candidate_kernel<<<blocks, 256, 0, st>>>(outputs, C, total_rows, w.cand_key, w.cand_cls);
-  }
-  if (int e = cuda_status(fn)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_score_kernel), 96 * 1024, fn)) return e;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel), 227 * 1024, fn)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel), 100 * 1024, fn)) return e;
   NmsParams p;
   p.outputs = outputs; p.P = P; p.C = C;
   p.cand_key = w.cand_key; p.cand_cls = w.cand_cls;
@@ -843,14 +833,14 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   p.order = order ? order : w.order; p.order_cnt = order_cnt;
   p.keep = keep ? keep : w.keep; p.keep_cnt = keep_cnt;
   p.trace = g_nms_trace;
-  // small-K images first (three per SM); whatever it flags as large goes through the tiled kernel (one per SM)
   const size_t small_smem = ((sizeof(SmallShared) + 15) & ~static_cast<size_t>(15)) + (static_cast<size_t>((P + 31) / 32) * 4 + 16);
-  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel), 100 * 1024, fn)) return e;
-  // Programmatic dependent launch: each grid may be scheduled while its predecessor drains and blocks in
-  // griddepcontrol.wait before touching the predecessor's results -- hides the launch latency between the kernels.
-  auto launch_pdl = [&](auto kernel, int threads, size_t dyn_smem, auto... args) -> int {
+  const bool use_small = small_smem <= 100 * 1024 && P <= kSmallWarps * 32 * kSmallRounds;
+
+  // Launch helper.  With `pdl` the grid may be scheduled while its predecessor in the stream is still running
+  // (programmatic dependent launch); kernels that consume the predecessor's results block in griddepcontrol.wait.
+  auto launch = [&](auto kernel, unsigned grid, int threads, size_t dyn_smem, bool pdl, auto... args) -> int {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(N));
+    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = dyn_smem;
     cfg.stream = st;
@@ -858,16 +848,45 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 1 : 0;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
     if (e != cudaSuccess) { set_error("%s: launch: %s", fn, cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
     return 0;
   };
-  if (small_smem <= 100 * 1024 && P <= kSmallWarps * 32 * kSmallRounds) {
-    if (int e = launch_pdl(nms_small_kernel, kSmallThreads, small_smem, p, w.large)) return e;
-    return launch_pdl(nms_kernel, kNmsThreads, smem, p, static_cast<const int32_t*>(w.large));
+
+  // The batch goes through in image-aligned parts: (decode+score | candidates)(k) -> nms_small(k).  The first stage of part
+  // k+1 does not depend on nms_small(k) (different images), so with programmatic launch the memory-bound pass over part
+  // k+1 runs on the same SMs under the compute-bound suppression of part k.  The very first launch is an ordinary one
+  // (it depends on whatever produced `outputs`), and so is the final tiled kernel, which reads the flags of every part.
+  // Measured on B200 (batch 256): splitting is a loss -- three resident NMS CTAs per SM leave room for a single
+  // decode CTA, which starves the memory-bound pass -- so the batch goes through as one part.
+  const int parts = 1;
+  for (int k = 0; k < parts; ++k) {
+    const int n0 = static_cast<int>(static_cast<long long>(N) * k / parts), n1 = static_cast<int>(static_cast<long long>(N) * (k + 1) / parts);
+    const int nk = n1 - n0;
+    if (nk <= 0) continue;
+    const size_t rows_k = static_cast<size_t>(nk) * P, off = static_cast<size_t>(n0) * P;
+    float* out_k = outputs + off * row;
+    if (fused) {
+      const unsigned blocks = static_cast<unsigned>((rows_k + kTileRows - 1) / kTileRows);
+      const size_t tile_bytes = static_cast<size_t>(kTileRows) * row * sizeof(float);
+      const int vec_ok = aligned16(out_k) && ((static_cast<size_t>(kTileRows) * row) % 4 == 0);
+      if (int e = launch(decode_score_kernel, blocks, kTileRows, tile_bytes, k > 0, out_k, reinterpret_cast<const float4*>(priors), P, C, rows_k,
+                         w.cand_key + off, w.cand_cls + off, vec_ok)) return e;
+    } else {
+      const unsigned blocks = static_cast<unsigned>(std::min<size_t>((rows_k + 7) / 8, 148 * 16));
+      if (int e = launch(candidate_kernel, blocks, 256, 0, k > 0, static_cast<const float*>(out_k), C, rows_k, w.cand_key + off, w.cand_cls + off)) return e;
+    }
+    if (use_small) {
+      NmsParams pk = p;
+      pk.outputs = out_k; pk.cand_key = w.cand_key + off; pk.cand_cls = w.cand_cls + off;
+      pk.order = p.order + off; pk.keep = p.keep + off;
+      pk.order_cnt = p.order_cnt ? p.order_cnt + n0 : nullptr;
+      pk.keep_cnt = p.keep_cnt ? p.keep_cnt + n0 : nullptr;
+      if (int e = launch(nms_small_kernel, static_cast<unsigned>(nk), kSmallThreads, small_smem, true, pk, w.large + n0)) return e;
+    }
   }
-  return launch_pdl(nms_kernel, kNmsThreads, smem, p, static_cast<const int32_t*>(nullptr));
+  return launch(nms_kernel, static_cast<unsigned>(N), kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
 }
 
 }  // namespace ssdh
