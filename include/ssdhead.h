@@ -148,6 +148,13 @@ SSDH_API int ssdh_postprocess(float* outputs, const float* priors, int N, int P,
                      int top_k, int per_class, int32_t* order, int32_t* order_cnt, int32_t* keep, int32_t* keep_cnt,
                      void* ws, size_t ws_bytes, ssdh_stream_t stream);
 
+/* "Next" row: compact detection lists instead of the dense in-place tensor.  For each image the kept rows
+ * (keep [N, P] i32 / keep_cnt [N] as written by ssdh_nms / ssdh_postprocess, score order) become rows
+ * [cx, cy, w, h, score, label] of dets [N, max_det, 6]; det_cnt [N] = min(keep_cnt, max_det); unused rows are zeroed.
+ * label is the 1-based class (column - 4); replaces the 8732-row Python loop of src/inference.py:77-81. */
+SSDH_API int ssdh_gather_detections(const float* outputs, const int32_t* keep, const int32_t* keep_cnt, int N, int P, int C,
+                           int max_det, float* dets, int32_t* det_cnt, ssdh_stream_t stream);
+
 /* E1+E2  TP/FP assignment, src/evaluate.py:31-42 and :132-151, accumulated as sufficient statistics.
  * outputs [N, P, 4+C] after NMS, gts [N, G, 4+C].  tallies [C-1, 3] i64 += {TP, detections, ground truths}
  * per class (atomic adds: zero it before the first batch).  tp_flags [N, P] u8 or NULL: 1 = true positive,

@@ -47,6 +47,7 @@ SIGNATURES = {
                          c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssdh_postprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ssdh_gather_detections": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ssdh_eval_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "ssdh_eval_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                      c_void_p, c_size_t, c_void_p]),

@@ -778,6 +778,41 @@ __global__ void __launch_bounds__(kSmallThreads, 3) nms_small_kernel(const NmsPa
   }
 }
 
+// Compact detection lists from the keep lists (one warp per detection slot).
+__global__ void __launch_bounds__(256)
+gather_detections_kernel(const float* __restrict__ outputs, const int32_t* __restrict__ keep, const int32_t* __restrict__ keep_cnt,
+                         int P, int C, int max_det, float* __restrict__ dets, int32_t* __restrict__ det_cnt) {
+  const int n = blockIdx.y, row = 4 + C;
+  const int lane = threadIdx.x & 31;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot >= max_det) return;
+  const int cnt = min(keep_cnt[n], max_det);
+  if (slot == 0 && lane == 0) det_cnt[n] = cnt;
+  float* out = dets + (static_cast<size_t>(n) * max_det + slot) * 6;
+  if (slot >= cnt) {
+    if (lane < 6) out[lane] = 0.0f;
+    return;
+  }
+  const int r = keep[static_cast<size_t>(n) * P + slot];
+  const float* src = outputs + (static_cast<size_t>(n) * P + r) * row;
+  // the kept row carries exactly one positive score among the non-void classes: find it with a ballot
+  float best = 0.0f;
+  int label = 0;
+  for (int c = 1 + lane; c < C; c += 32) {
+    const float v = src[4 + c];
+    if (v > best) { best = v; label = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ol = __shfl_xor_sync(0xffffffffu, label, o);
+    if (ov > best || (ov == best && ol != 0 && (label == 0 || ol < label))) { best = ov; label = ol; }
+  }
+  if (lane < 4) out[lane] = src[lane];
+  if (lane == 4) out[4] = best;
+  if (lane == 5) out[5] = static_cast<float>(label);
+}
+
 static size_t nms_smem_bytes(int P) {
   const size_t Pp = (static_cast<size_t>(P) + 15) & ~static_cast<size_t>(15);
   const size_t head = ((sizeof(NmsShared) + 15) & ~static_cast<size_t>(15)) + ((static_cast<size_t>((P + 31) / 32) * 4 + 15) & ~static_cast<size_t>(15));
@@ -918,6 +953,14 @@ extern "C" int ssdh_iou(const float* t, int t_row_stride, int T, const float* s,
 }
 
 extern "C" __attribute__((visibility("default"))) void ssdh_debug_set_nms_trace(unsigned long long* buf) { g_nms_trace = buf; }
+
+extern "C" int ssdh_gather_detections(const float* outputs, const int32_t* keep, const int32_t* keep_cnt, int N, int P, int C,
+                                      int max_det, float* dets, int32_t* det_cnt, ssdh_stream_t stream) {
+  if (!outputs || !keep || !keep_cnt || !dets || !det_cnt || N <= 0 || P <= 0 || C <= 1 || max_det <= 0) { set_error("ssdh_gather_detections: bad argument"); return SSDH_E_ARG; }
+  const dim3 grid(static_cast<unsigned>((static_cast<size_t>(max_det) * 32 + 255) / 256), static_cast<unsigned>(N));
+  gather_detections_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(outputs, keep, keep_cnt, P, C, max_det, dets, det_cnt);
+  return cuda_status("ssdh_gather_detections");
+}
 
 extern "C" size_t ssdh_nms_workspace_bytes(int N, int P, int C) {
   (void)C;

@@ -343,6 +343,21 @@ def postprocess_(outputs: torch.Tensor, priors: torch.Tensor, iou_thresh: float 
     return _nms_call("postprocess_", outputs, priors, iou_thresh, score_thresh, top_k, per_class, want_lists)
 
 
+def gather_detections(outputs: torch.Tensor, keep: torch.Tensor, keep_cnt: torch.Tensor, max_det: int = 200):
+    """Compact per-image detection lists: (dets (N, max_det, 6) = [cx, cy, w, h, score, label], det_cnt (N,) int32)."""
+    lib = _lib.load()
+    _need_cuda(outputs, keep, keep_cnt)
+    outputs = _f32c(outputs)
+    N, P, row = outputs.shape
+    dets = torch.empty(N, max_det, 6, dtype=torch.float32, device=outputs.device)
+    cnt = torch.empty(N, dtype=torch.int32, device=outputs.device)
+    if N > 0:
+        with torch.cuda.device(outputs.device):
+            check(lib.ssdh_gather_detections(outputs.data_ptr(), keep.contiguous().data_ptr(), keep_cnt.contiguous().data_ptr(), N, P, row - 4,
+                                             int(max_det), dets.data_ptr(), cnt.data_ptr(), _stream()), "ssdh_gather_detections")
+    return dets, cnt
+
+
 # ------------------------------------------------------------------------------------------------ E1-E2
 def eval_accumulate(outputs: torch.Tensor, gts: torch.Tensor, tallies: Optional[torch.Tensor] = None, iou_thresh: float = 0.5,
                     want_flags: bool = False):

@@ -49,3 +49,12 @@ def postprocess(outputs: torch.Tensor, df: torch.Tensor, iou_thresh: float = 0.5
     ops.postprocess_(work, df, iou_thresh, score_thresh, top_k, per_class)
     outputs.copy_(work)
     return outputs
+
+
+def detect(outputs: torch.Tensor, df: torch.Tensor, iou_thresh: float = 0.5, score_thresh: float = 0.0, top_k: Optional[int] = 200,
+           per_class: bool = False):
+    """Raw head output -> compact detections: ``postprocess`` in place, then the kept rows of every image
+    as ``dets (N, top_k, 6) = [cx, cy, w, h, score, label]`` in descending score order plus ``det_cnt (N,)``.
+    Replaces the dense tensor walk of reference src/inference.py:71-81."""
+    res = ops.postprocess_(outputs, df, iou_thresh, score_thresh, top_k, per_class, want_lists=True)
+    return ops.gather_detections(outputs, res.keep, res.keep_cnt, max_det=int(top_k or outputs.shape[1]))

@@ -20,5 +20,5 @@ restatement against the committed fixtures everywhere else (including the GPU bo
 from .head import (  # noqa: F401
     default_boxes, pair_iou_match, match_mask, encode_offsets, smooth_l1, split_pos_neg,
     kplus1_threshold, multibox_loss, decode_boxes, class_scores, pair_iou, greedy_nms,
-    nms_inplace, class_order, eval_image_class, eval_batch, average_precision,
+    nms_inplace, class_order, eval_image_class, eval_batch, average_precision, voc_ap_numpy,
 )

@@ -336,3 +336,27 @@ def average_precision(result: torch.Tensor, count) -> torch.Tensor:
     envelope = torch.flip(torch.cummax(torch.flip(padded, dims=[0]), dim=0).values, dims=[0])
     rec = torch.cat([zero, recall, torch.ones(1)])
     return torch.sum(envelope[1:] * (rec[1:] - rec[:-1]))
+
+
+# ----------------------------------------------------------------------------------------
+# Opt-in extension: true PASCAL VOC AP (not in the reference).  Plain numpy.
+# ----------------------------------------------------------------------------------------
+def voc_ap_numpy(scores, tp, n_gt: int, use_07_metric: bool = False) -> float:
+    import numpy as np
+    scores, tp = np.asarray(scores, dtype=np.float64), np.asarray(tp, dtype=np.float64)
+    if n_gt <= 0:
+        return float("nan")
+    if scores.size == 0:
+        return 0.0
+    order = np.argsort(-scores, kind="stable")
+    hit = tp[order]
+    tps, fps = np.cumsum(hit), np.cumsum(1.0 - hit)
+    rec, prec = tps / n_gt, tps / np.maximum(tps + fps, 1e-12)
+    if use_07_metric:
+        return float(sum((prec[rec >= t].max() if (rec >= t).any() else 0.0) for t in np.arange(0.0, 1.1, 0.1)) / 11.0)
+    mrec = np.concatenate([[0.0], rec, [1.0]])
+    mpre = np.concatenate([[0.0], prec, [0.0]])
+    for i in range(mpre.size - 2, -1, -1):
+        mpre[i] = max(mpre[i], mpre[i + 1])
+    idx = np.where(mrec[1:] != mrec[:-1])[0]
+    return float(((mrec[idx + 1] - mrec[idx]) * mpre[idx + 1]).sum())

@@ -73,6 +73,26 @@ def test_host_side_eval_helpers(priors_cpu):
     assert evaluate.get_order(rows, 3).tolist() == [3, 1, 4] == head.class_order(rows, 3).tolist()
 
 
+def test_voc_average_precision_matches_numpy_oracle():
+    from object_detection_torch2_b200 import evaluate
+    from oracle import head
+    g = torch.Generator().manual_seed(9)
+    for trial in range(12):
+        n = int(torch.randint(0, 60, (1,), generator=g))
+        scores = torch.rand(n, generator=g)
+        if n > 4:
+            scores[1] = scores[3]                      # a tie: stable order
+        tp = (torch.rand(n, generator=g) > 0.5).float()
+        n_gt = int(torch.randint(1, 40, (1,), generator=g))
+        for m07 in (False, True):
+            got = float(evaluate.voc_average_precision(scores, tp, n_gt, m07))
+            assert got == pytest.approx(head.voc_ap_numpy(scores.numpy(), tp.numpy(), n_gt, m07), rel=1e-6, abs=1e-7)
+    assert torch.isnan(evaluate.voc_average_precision(torch.rand(3), torch.ones(3), 0))
+    # perfect ranking -> AP 1; all misses -> 0
+    assert float(evaluate.voc_average_precision(torch.tensor([.9, .8]), torch.ones(2), 2)) == pytest.approx(1.0)
+    assert float(evaluate.voc_average_precision(torch.tensor([.9, .8]), torch.zeros(2), 2)) == 0.0
+
+
 def test_shard_bounds():
     from object_detection_torch2_b200 import parallel
     for n, w in ((1024, 8), (4952, 8), (5, 4), (3, 8)):

@@ -189,3 +189,37 @@ def test_eval_planted_vs_oracle(priors_cpu):
     res = torch.tensor([[1., .9], [0., .8], [1., .7], [0., .6]])
     assert float(evaluate.calc_average_precision(res.to(DEV), 4)) == pytest.approx(float(head.average_precision(res, 4)))
     assert evaluate.get_order(x[0].to(DEV), 3).cpu().tolist() == head.class_order(x[0], 3).tolist()
+
+
+def test_compact_detections_and_voc_ap(priors_cpu, priors_gpu):
+    # "next" rows: compact detection lists and the true VOC AP, against the oracle pipeline
+    o, t = synth.make_batch(6, 171, "D2", 10)
+    o = synth.plant_detections(o, t, priors_cpu, 171, per_gt=4, jitter=0.3)
+    x, keeps = head.nms_inplace(scored_cpu(o, priors_cpu))
+    xd = x.to(DEV)
+    res = ops.nms_(scored_cpu(o, priors_cpu).to(DEV), want_lists=True)
+    dets, cnt = ops.gather_detections(xd, res.keep, res.keep_cnt, max_det=100)
+    for n in range(6):
+        k = min(len(keeps[n]), 100)
+        assert int(cnt[n]) == k
+        rows = x[n, keeps[n][:k]]
+        assert torch.equal(dets[n, :k, :4].cpu(), rows[:, :4])
+        assert torch.equal(dets[n, :k, 4].cpu(), rows[:, 5:].max(dim=1).values)
+        assert torch.equal(dets[n, :k, 5].cpu().long(), rows[:, 4:].argmax(dim=1))
+        assert float(dets[n, k:].abs().sum()) == 0.0
+    d2, c2 = utils.detect(o.to(DEV), priors_gpu, top_k=50)
+    assert d2.shape == (6, 50, 6) and int(c2.max()) <= 50 and bool((d2[:, :, 4][:, :-1] >= d2[:, :, 4][:, 1:]).all())
+    ev = evaluate.DetectionEvaluator()
+    ev.update(xd[:3], t[:3].to(DEV))
+    ev.update(xd[3:], t[3:].to(DEV))
+    out = ev.compute()
+    tallies, results = head.eval_batch(x, t)
+    assert torch.equal(out["tallies"].cpu(), tallies)
+    for c in range(20):
+        if results[c]:
+            r = torch.cat(results[c])
+            want = head.voc_ap_numpy(r[:, 1].numpy(), r[:, 0].numpy(), int(tallies[c, 2]))
+        else:
+            want = float("nan") if int(tallies[c, 2]) == 0 else 0.0
+        got = float(out["ap_voc"][c])
+        assert (np.isnan(want) and np.isnan(got)) or got == pytest.approx(want, rel=1e-5, abs=1e-6), (c, got, want)
