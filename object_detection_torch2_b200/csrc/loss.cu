@@ -635,31 +635,28 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       __syncthreads();
       trace_point(p, 18);
       if (total <= 256) {
-        // few candidates (the usual case): exact order statistic by counting, spread over the whole CTA.  Thread t
-        // compares candidate t % 256 with one third of the list and adds its partial counts; the (rem+1)-th largest
-        // is the key with  above <= rem < above + equal.  tot[] / hist[1][] are zero here (see above).
+        // few candidates (the usual case): exact order statistic by counting, spread over the whole CTA.  With
+        // above(v) = #{candidates > v}, the (rem+1)-th largest is the SMALLEST key whose above() is <= rem.  Thread t
+        // compares candidate t % 256 with one part of the list and adds its partial count (tot[] is zero here).
         uint32_t* cnt_above = &sh.tot[0][0];
-        uint32_t* cnt_equal = &sh.hist[1][0][0];
         constexpr int kParts = kLossThreads / 256;                 // 3 with 768 threads, 1 with 384
         const int ci = tid & 255, part = tid >> 8;
+        if (tid == 0) sh.sel_prefix = 0xffffffffu;
         if (ci < total && part < kParts) {
           const uint32_t mine = sh.gathered[ci];
-          const int per = (total + kParts - 1) / kParts;
+          const int per = (((total + kParts - 1) / kParts) + 3) & ~3;
           const int j0 = part * per, j1 = min(total, j0 + per);
-          int above = 0, equal = 0;
-          for (int j = j0; j < j1; ++j) {
-            const uint32_t v = sh.gathered[j];
-            above += v > mine;
-            equal += v == mine;
+          int above = 0;
+          int j = j0;
+          for (; j + 4 <= j1; j += 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(&sh.gathered[j]);
+            above += (v.x > mine) + (v.y > mine) + (v.z > mine) + (v.w > mine);
           }
+          for (; j < j1; ++j) above += sh.gathered[j] > mine;
           if (above) atomicAdd(&cnt_above[ci], static_cast<uint32_t>(above));
-          if (equal) atomicAdd(&cnt_equal[ci], static_cast<uint32_t>(equal));
         }
         __syncthreads();
-        if (tid < total) {
-          const uint32_t above = cnt_above[tid], equal = cnt_equal[tid];
-          if (above <= rem && rem < above + equal) sh.sel_prefix = sh.gathered[tid];
-        }
+        if (tid < total && cnt_above[tid] <= rem) atomicMin(&sh.sel_prefix, sh.gathered[tid]);
         __syncthreads();
         prefix = sh.sel_prefix;
       } else {

@@ -37,5 +37,7 @@ for i, nm in enumerate(names):
     col = rel[:, i]
     print("%-22s median %8.0f  p10 %8.0f  max %8.0f   +%.0f" % (nm, np.median(col), np.percentile(col, 10), col.max(), np.median(col - prev)))
     prev = col
+sel = tr[:, 16:19].astype(np.float64) - clk[:, :1]
+print("select detail (median cycles since CTA start): list built %.0f, csync %.0f, gathered %.0f" % tuple(np.median(sel, axis=0)))
 g0, g1 = tr[:, 0], tr[:, 14]
 print("step 6: first start -> last end %.2f us; gap from step 5 last end to step 6 first start %.2f us" % ((g1.max() - g0.min()) / 1e3, (g0.min() - tr5[:, 14].max()) / 1e3))
