@@ -36,6 +36,16 @@ constexpr int kGatherCap = 768;      // cluster-wide candidates finished locally
 //   <768, 4>: 4 CTAs x ~221 KB per image, one CTA per SM  -> every SM carries the same load (default when it fits)
 //   <384, 8>: 8 CTAs x ~110 KB per image                   -> larger images / more ground truth per image
 
+// Workspace record of one image.  The layout is independent of N so that the ticket words of a cached workspace are
+// always found zero again (they are reset by their last user), whatever batch size the previous call had.
+struct ImageSlot {          // 112 bytes
+  double part_loss[kMaxCluster];   // per-CTA partial sums
+  double image_loss;               // inv_pos * sum, ssd.py:227 before .mean()
+  int part_sel[kMaxCluster];       // selected positives | selected negatives << 16
+  unsigned int ticket;             // CTAs of this image that have delivered their partial
+  unsigned int pad;
+};
+
 struct LossParams {
   const float* outputs;
   const float* targets;
@@ -50,7 +60,7 @@ struct LossParams {
   float* grad;
   ssdh_image_stats* stats;
   unsigned int* ticket;   // workspace: zero before first use, left zero
-  double* image_loss;     // workspace [N]
+  ImageSlot* slots;       // workspace [N]: per-CTA partial sums of one image + its arrival ticket (left zero)
   int rows_per_cta;       // shared-memory rows reserved per CTA (multiple of kBlockRows)
   int n_blocks;           // ceil(P / kBlockRows)
   int bulk;               // 1: every block is 16-byte aligned/sized -> TMA path
@@ -84,8 +94,6 @@ struct LossShared {
   unsigned long long mbar[kSlots][kMaxLossWarps];   // one per (row slot, warp): a warp's 32 rows are one dealt block
   uint8_t gt_fast[kMaxGT], gt_slow[kMaxGT];          // ground-truth rows by matching path (see the match section)
   int n_fast, n_slow, soft_labels;
-  double part_loss[kMaxCluster];          // leader only: written remotely by every CTA
-  int part_pos_sel[kMaxCluster], part_neg_sel[kMaxCluster];
   double wred_loss[kMaxLossWarps];
   int wred_a[kMaxLossWarps], wred_b[kMaxLossWarps];
   int pos_local, list_cnt;                // read remotely
@@ -718,6 +726,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     sel_key = prefix;
     if (tid == 0) sh.overflow = over;
   }
+  cluster.barrier_arrive();     // last access to distributed shared memory is behind us; the matching wait is at kernel end
   trace_point(p, 8);
   const float thr_sel = need_select ? key_float(sel_key) : 0.0f;
   const float thr_pos = sel_set == 0 ? thr_sel : 0.0f;
@@ -726,7 +735,10 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   const float inv_pos = k_pos > 0 ? __fdiv_rn(1.0f, static_cast<float>(k_pos)) : 0.0f;     // ssd.py:226
 
   // ---- masked sums (ssd.py:227) ---------------------------------------------------------------------------
+  // The CTA's partial goes to a global slot; the LAST of the image's CTAs to arrive (ticket) adds the partials in rank
+  // order -- deterministic, and nobody waits: the other CTAs go straight on to their gradient rows.
   bool sel[kSlots];
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // first global writes below: the previous grid (same workspace) is complete
   {
     float accf = 0.0f;
     int cnt2 = 0;                            // selected positives | selected negatives << 16
@@ -749,39 +761,44 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       t = warp_sum(t);                      // fixed shuffle tree: deterministic
       c2 = warp_sum(c2);
       if (lane == 0) {
-        *cluster.map_shared_rank(&sh.part_loss[rank], 0) = t;
-        *cluster.map_shared_rank(&sh.part_pos_sel[rank], 0) = c2 & 0xffff;
-        *cluster.map_shared_rank(&sh.part_neg_sel[rank], 0) = c2 >> 16;
+        ImageSlot* slot = p.slots + n;
+        slot->part_loss[rank] = t;
+        slot->part_sel[rank] = c2;
+        __threadfence();
+        const unsigned int arrived = atomicAdd(&slot->ticket, 1u);
+        if (arrived == static_cast<unsigned int>(kCluster) - 1u) {
+          __threadfence();
+          double total = 0.0;
+          int pos_sel = 0, neg_sel = 0;
+          for (int r = 0; r < kCluster; ++r) {
+            total += __ldcg(&slot->part_loss[r]);
+            const int c = __ldcg(&slot->part_sel[r]);
+            pos_sel += c & 0xffff;
+            neg_sel += c >> 16;
+          }
+          slot->ticket = 0u;
+          const float li = static_cast<float>(total) * inv_pos;
+          if (p.stats) {
+            ssdh_image_stats st;
+            st.loss = li; st.thr_pos = thr_pos; st.thr_neg = thr_neg;
+            st.pos_raw = sh.pos_raw; st.k_pos = k_pos; st.k_neg = sh.k_neg; st.pos_sel = pos_sel; st.neg_sel = neg_sel;
+            p.stats[n] = st;
+          }
+          slot->image_loss = static_cast<double>(li);
+          __threadfence();
+          const unsigned int done = atomicAdd(p.ticket, 1u);
+          if (done == static_cast<unsigned int>(p.N) - 1u) {
+            __threadfence();
+            double sum = 0.0;
+            for (int i = 0; i < p.N; ++i) sum += __ldcg(&p.slots[i].image_loss);      // fixed order -> deterministic
+            *p.loss = static_cast<float>(sum * static_cast<double>(p.inv_n_global));
+            *p.ticket = 0u;
+          }
+        }
       }
     }
   }
-
-  // ---- cluster exchange #2: per-image loss, stats, batch mean ----------------------------------------------------
-  asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous grid (same workspace, maybe same outputs) is complete
-  cluster.sync();          // last use of distributed shared memory: CTAs are independent from here on
   trace_point(p, 9);
-  if (rank == 0 && tid == 0) {
-    double total = 0.0;
-    int pos_sel = 0, neg_sel = 0;
-    for (int r = 0; r < kCluster; ++r) { total += sh.part_loss[r]; pos_sel += sh.part_pos_sel[r]; neg_sel += sh.part_neg_sel[r]; }
-    const float li = static_cast<float>(total) * inv_pos;
-    if (p.stats) {
-      ssdh_image_stats st;
-      st.loss = li; st.thr_pos = thr_pos; st.thr_neg = thr_neg;
-      st.pos_raw = sh.pos_raw; st.k_pos = k_pos; st.k_neg = sh.k_neg; st.pos_sel = pos_sel; st.neg_sel = neg_sel;
-      p.stats[n] = st;
-    }
-    p.image_loss[n] = static_cast<double>(li);
-    __threadfence();
-    const unsigned int t = atomicAdd(p.ticket, 1u);
-    if (t == static_cast<unsigned int>(p.N) - 1u) {
-      __threadfence();
-      double sum = 0.0;
-      for (int i = 0; i < p.N; ++i) sum += __ldcg(p.image_loss + i);      // fixed order -> deterministic
-      *p.loss = static_cast<float>(sum * static_cast<double>(p.inv_n_global));
-      *p.ticket = 0u;
-    }
-  }
   // ---- gradient rows, in place over the slab, then out by TMA -------------------------------------------------
   if (p.grad != nullptr) {
     const float sn = inv_pos * p.inv_n_global;          // d loss / d (per-image sum)
@@ -857,6 +874,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
 
   trace_point(p, 10);
   if (p.bulk && p.grad != nullptr && lane == 0) bulk_store_wait();
+  cluster.barrier_wait();       // my shared memory may be read by cluster peers until they have all passed their selection
   trace_point(p, 11);
   trace_point(p, 12);
   if (p.trace != nullptr && tid == 0) {
@@ -939,7 +957,7 @@ using namespace ssdh;
 
 extern "C" size_t ssdh_multibox_loss_workspace_bytes(int N, int P, int C, int G) {
   (void)P; (void)C; (void)G;
-  return 16 + static_cast<size_t>(N > 0 ? N : 0) * sizeof(double);
+  return 16 + static_cast<size_t>(N > 0 ? N : 0) * sizeof(ImageSlot);
 }
 
 static int multibox_loss_impl(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
@@ -972,7 +990,7 @@ static int multibox_loss_impl(const float* outputs, const float* targets, const 
   p.inv_n_global = 1.0f / static_cast<float>(n_global);
   p.loss = loss; p.grad = grad; p.stats = stats;
   p.ticket = reinterpret_cast<unsigned int*>(ws);
-  p.image_loss = reinterpret_cast<double*>(static_cast<unsigned char*>(ws) + 16);
+  p.slots = reinterpret_cast<ImageSlot*>(static_cast<unsigned char*>(ws) + 16);
   p.rows_per_cta = shape.rows_per_cta;
   p.n_blocks = blocks_for(P);
   // TMA bulk copies need 16-byte aligned addresses and sizes for every (image, CTA, slot) chunk.
