@@ -27,7 +27,8 @@ namespace cg = cooperative_groups;
 namespace ssdh {
 
 constexpr int kSlots = 3;            // rows per thread
-constexpr int kBlockRows = 32;       // rows per dealt block (one warp-row)
+constexpr int kBlockRows = 32;       // rows per row slot of a warp
+constexpr int kChunkRows = kSlots * kBlockRows;   // rows dealt to one warp: 96 contiguous rows = one TMA copy in, three out
 constexpr int kMaxCluster = 8;
 constexpr int kMaxLossWarps = 32;
 constexpr int kListCap = 384;        // per-CTA candidates of the selected bucket
@@ -61,8 +62,8 @@ struct LossParams {
   ssdh_image_stats* stats;
   unsigned int* ticket;   // workspace: zero before first use, left zero
   ImageSlot* slots;       // workspace [N]: per-CTA partial sums of one image + its arrival ticket (left zero)
-  int rows_per_cta;       // shared-memory rows reserved per CTA (multiple of kBlockRows)
-  int n_blocks;           // ceil(P / kBlockRows)
+  int rows_per_cta;       // shared-memory rows reserved per CTA (multiple of kChunkRows)
+  int n_chunks;           // ceil(P / kChunkRows)
   int bulk;               // 1: every block is 16-byte aligned/sized -> TMA path
   unsigned long long* trace;   // debug: [grid][kTracePoints] SM clock stamps (NULL in production)
 };
@@ -253,7 +254,6 @@ __device__ __forceinline__ void hist_add(uint32_t* hist_set0, bool active, int s
 template <int kC, int kLossThreads, int kCluster>
 __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const LossParams p) {
   constexpr int kLossWarps = kLossThreads / 32;
-  constexpr int kSlotBlocks = kLossThreads / kBlockRows;      // dealt blocks per row slot
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = static_cast<int>(cluster.block_rank());
   const int n = blockIdx.x / kCluster;
@@ -262,8 +262,12 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   const int G = p.G;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  // CTA `rank` owns global blocks rank, rank + kCluster, ...; local block j <-> global block j * kCluster + rank
-  const int my_blocks = (p.n_blocks - rank + kCluster - 1) / kCluster;
+  // The image is cut into 96-row chunks dealt round-robin to the CTAs of the cluster (every CTA sees the same mix of
+  // prior levels); inside a CTA, warp w owns local chunk w: global chunk w * kCluster + rank, rows [32 s, 32 s + 32) of
+  // it are the warp's row slot s.  One TMA copy brings the chunk in, one per slot takes the gradient out.
+  const int my_chunks = (p.n_chunks - rank + kCluster - 1) / kCluster;
+  const int my_chunk = warp * kCluster + rank;                                   // global chunk of this warp
+  const int my_rows_w = warp < my_chunks ? min(kChunkRows, p.P - my_chunk * kChunkRows) : 0;   // rows this warp owns
   constexpr float kLog2e = 1.4426950408889634f;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -286,9 +290,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   bool valid[kSlots];
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) {
-    const int lr = s * kLossThreads + tid;
-    const int grow = (((lr >> 5) * kCluster + rank) << 5) + (lr & 31);
-    valid[s] = ((lr >> 5) < my_blocks) && (grow < p.P);
+    const int grow = my_chunk * kChunkRows + s * kBlockRows + lane;
+    valid[s] = s * kBlockRows + lane < my_rows_w;
     pri[s] = __ldg(p.priors + (valid[s] ? grow : 0));
   }
   if (tid == 0) {
@@ -344,35 +347,23 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   }
   __syncthreads();
 
-  // ---- slab: every warp fetches its own dealt blocks (one per row slot) by TMA bulk copy onto its own mbarriers;
-  // issued only now, after the ground truth landed, so the small loads were never queued behind this traffic ----
+  // ---- slab: every warp fetches its own 96-row chunk with ONE TMA bulk copy onto its own mbarrier; issued only now,
+  // after the ground truth landed, so the small loads were never queued behind this traffic ---------------------------
+  float* my_slab = slab + static_cast<size_t>(warp) * kChunkRows * row;
   if (p.bulk) {
-    if (lane < kSlots) {                              // lane s initialises, arms and issues slot s: three copies in flight at once
-      const int s = lane;
-      mbar_init(&sh.mbar[s][warp], 1);
+    if (lane == 0) {
+      mbar_init(&sh.mbar[0][warp], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      const int j = s * kSlotBlocks + warp;
-      if (j < my_blocks) {
-        const int gb = j * kCluster + rank;
-        const uint32_t bytes = static_cast<uint32_t>(min(kBlockRows, p.P - gb * kBlockRows)) * row * sizeof(float);
-        mbar_expect_tx(&sh.mbar[s][warp], bytes);
-        bulk_load_hint(slab + static_cast<size_t>(j) * kBlockRows * row, img_in + static_cast<size_t>(gb) * kBlockRows * row, bytes,
-                       &sh.mbar[s][warp], policy_evict_first());
+      if (my_rows_w > 0) {
+        const uint32_t bytes = static_cast<uint32_t>(my_rows_w) * row * sizeof(float);
+        mbar_expect_tx(&sh.mbar[0][warp], bytes);
+        bulk_load_hint(my_slab, img_in + static_cast<size_t>(my_chunk) * kChunkRows * row, bytes, &sh.mbar[0][warp], policy_evict_first());
       }
     }
     __syncwarp();
   } else {
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-      const int j = s * kSlotBlocks + warp;
-      if (j < my_blocks) {
-        const int gb = j * kCluster + rank;
-        const int nfl = min(kBlockRows, p.P - gb * kBlockRows) * row;
-        const float* src = img_in + static_cast<size_t>(gb) * kBlockRows * row;
-        float* dst = slab + static_cast<size_t>(j) * kBlockRows * row;
-        for (int i = lane; i < nfl; i += 32) dst[i] = src[i];
-      }
-    }
+    const float* src = img_in + static_cast<size_t>(my_chunk) * kChunkRows * row;
+    for (int i = lane; i < my_rows_w * row; i += 32) my_slab[i] = src[i];
     __syncwarp();
   }
 
@@ -455,11 +446,10 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) {
     ce[s] = 0.0f; lloc[s] = 0.0f; lse[s] = 0.0f;
-    if (s * kSlotBlocks + warp >= my_blocks) continue;              // uniform per warp
-    if (p.bulk) mbar_wait(&sh.mbar[s][warp], 0);
+    if (s * kBlockRows >= my_rows_w) continue;                      // uniform per warp
+    if (p.bulk && s == 0) mbar_wait(&sh.mbar[0][warp], 0);          // the whole chunk lands on one barrier
     if (s == 0) trace_point(p, 4);
-    const int lr = s * kLossThreads + tid;
-    float* rp = slab + static_cast<size_t>(lr) * row;
+    float* rp = my_slab + static_cast<size_t>(s * kBlockRows + lane) * row;
     if (valid[s]) {
       float mx, sum = 0.0f;
       if (kC > 0) {
@@ -542,14 +532,10 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
 
   // ---- software pipelining across micro-batches: HBM goes quiet from here until the gradient leaves, so every
   // warp now asks the L2 for the same blocks of the NEXT batch (this SM will read them again in the next launch) ------
-  if (p.next_outputs != nullptr && p.bulk && lane < kSlots) {
-    const int j = lane * kSlotBlocks + warp;
-    if (j < my_blocks) {
-      const int gb = j * kCluster + rank;
-      const uint32_t bytes = static_cast<uint32_t>(min(kBlockRows, p.P - gb * kBlockRows)) * row * sizeof(float);
-      const float* nsrc = p.next_outputs + static_cast<size_t>(n) * p.P * row + static_cast<size_t>(gb) * kBlockRows * row;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc), "r"(bytes) : "memory");
-    }
+  if (p.next_outputs != nullptr && p.bulk && lane == 0 && my_rows_w > 0) {
+    const uint32_t bytes = static_cast<uint32_t>(my_rows_w) * row * sizeof(float);
+    const float* nsrc = p.next_outputs + static_cast<size_t>(n) * p.P * row + static_cast<size_t>(my_chunk) * kChunkRows * row;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc), "r"(bytes) : "memory");
   }
   if (p.next_targets != nullptr && rank == 0 && tid == 32 && G > 0) {
     const uint32_t bytes = (static_cast<uint32_t>(G) * row * sizeof(float)) & ~15u;
@@ -608,7 +594,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     const uint32_t bucket = sh.sel_prefix;
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
-      if (s * kSlotBlocks + warp >= my_blocks) continue;           // uniform per warp
+      if (s * kBlockRows >= my_rows_w) continue;                    // uniform per warp
       const uint32_t key = float_key(ce[s]);
       const bool member = valid[s] && (((mlo[s] | mhi[s]) != 0u) == (sel_set == 0)) && (bucket_of(key) == bucket);
       const uint32_t ballot = __ballot_sync(0xffffffffu, member);
@@ -703,7 +689,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
         const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
-          if (s * kSlotBlocks + warp >= my_blocks) continue;
+          if (s * kBlockRows >= my_rows_w) continue;
           const uint32_t key = float_key(ce[s]);
           const bool member = valid[s] && (((mlo[s] | mhi[s]) != 0u) == (sel_set == 0)) && ((key & himask) == prefix);
           hist_add(&sh.hist[buf][0][0], member, sel_set, (key >> shift) & 255u, lane);
@@ -805,10 +791,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     float* img_out = p.grad + static_cast<size_t>(n) * p.P * row;
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
-      const int j = s * kSlotBlocks + warp;
-      if (j >= my_blocks) continue;                                 // uniform per warp
-      const int lr = s * kLossThreads + tid;
-      float* rp = slab + static_cast<size_t>(lr) * row;
+      if (s * kBlockRows >= my_rows_w) continue;                    // uniform per warp
+      float* rp = my_slab + static_cast<size_t>(s * kBlockRows + lane) * row;
       // One code path for every lane: row <- scale * softmax(row) with scale = s_n * (sum of matched class weights)
       // for a selected positive, s_n for a selected negative and 0 for an unselected row (exact zeros); then the
       // one-hot corrections.  Warps without any selected row (the common case late in training) just clear.
@@ -854,10 +838,9 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
           }
         }
       }
-      const int gb = j * kCluster + rank;
-      const int rows_b = min(kBlockRows, p.P - gb * kBlockRows);
-      float* dst = img_out + static_cast<size_t>(gb) * kBlockRows * row;
-      const float* srcb = slab + static_cast<size_t>(j) * kBlockRows * row;
+      const int rows_b = min(kBlockRows, my_rows_w - s * kBlockRows);
+      float* dst = img_out + (static_cast<size_t>(my_chunk) * kChunkRows + s * kBlockRows) * row;
+      const float* srcb = my_slab + static_cast<size_t>(s) * kBlockRows * row;
       if (p.bulk) {
         fence_async_smem();               // my generic-proxy writes -> visible to the TMA engine
         __syncwarp();
@@ -896,10 +879,10 @@ static size_t loss_smem_bytes(int rows_per_cta, int row, int G) {
   return slab + gt + sizeof(LossShared);
 }
 
-static int blocks_for(int P) { return (P + kBlockRows - 1) / kBlockRows; }
+static int chunks_for(int P) { return (P + kChunkRows - 1) / kChunkRows; }
 
 static int rows_per_cta_for(int P, int cluster) {          // shared-memory rows of the busiest CTA
-  return ((blocks_for(P) + cluster - 1) / cluster) * kBlockRows;
+  return ((chunks_for(P) + cluster - 1) / cluster) * kChunkRows;
 }
 
 constexpr size_t kMaxDynSmem = 227 * 1024;
@@ -992,7 +975,7 @@ static int multibox_loss_impl(const float* outputs, const float* targets, const 
   p.ticket = reinterpret_cast<unsigned int*>(ws);
   p.slots = reinterpret_cast<ImageSlot*>(static_cast<unsigned char*>(ws) + 16);
   p.rows_per_cta = shape.rows_per_cta;
-  p.n_blocks = blocks_for(P);
+  p.n_chunks = chunks_for(P);
   // TMA bulk copies need 16-byte aligned addresses and sizes for every (image, CTA, slot) chunk.
   const bool sizes_ok = (static_cast<long long>(P) * row) % 4 == 0;     // full blocks are 32 rows; only the tail block can be odd
   p.bulk = sizes_ok && aligned16(outputs) && (grad == nullptr || aligned16(grad));
