@@ -507,8 +507,10 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
             const float x1 = l1 - (r.cy - q.y) * rdh;
             const float x2 = l2 - ((r.flags & 1) ? r.lw - ldw : r.lw);
             const float x3 = l3 - ((r.flags & 2) ? r.lh - ldh : r.lh);
-            acc_loc += ((smooth_l1_f(x0) + smooth_l1_f(x1)) + smooth_l1_f(x2)) + smooth_l1_f(x3);
-            g0 += clamp1(x0); g1 += clamp1(x1); g2 += clamp1(x2); g3 += clamp1(x3);
+            // with c = clamp(x, -1, 1): smooth_l1(x) = c * (x - c / 2)  (ssd.py:283) and c is its derivative
+            const float c0 = clamp1(x0), c1 = clamp1(x1), c2 = clamp1(x2), c3 = clamp1(x3);
+            acc_loc += (c0 * fmaf(-0.5f, c0, x0) + c1 * fmaf(-0.5f, c1, x1)) + (c2 * fmaf(-0.5f, c2, x2) + c3 * fmaf(-0.5f, c3, x3));
+            g0 += c0; g1 += c1; g2 += c2; g3 += c3;
           }
         }
         ce[s] = acc_ce;
