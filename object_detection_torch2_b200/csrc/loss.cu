@@ -532,6 +532,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     if (lane == 0 && c) atomicAdd(&sh.pos_local, c);
   }
 
+  if (p.trace != nullptr && lane == 0) p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 24 + warp] = clock64();   // per-warp end of the row phase
+
   // ---- software pipelining across micro-batches: HBM goes quiet from here until the gradient leaves, so every
   // warp now asks the L2 for the same blocks of the NEXT batch (this SM will read them again in the next launch) ------
   if (p.next_outputs != nullptr && p.bulk && lane == 0 && my_rows_w > 0) {

@@ -39,5 +39,8 @@ for i, nm in enumerate(names):
     prev = col
 sel = tr[:, 16:19].astype(np.float64) - clk[:, :1]
 print("select detail (median cycles since CTA start): list built %.0f, csync %.0f, gathered %.0f" % tuple(np.median(sel, axis=0)))
+w = tr[:, 24:48].astype(np.float64) - clk[:, :1]
+print("row phase end per warp (median over CTAs, cycles since CTA start):", np.median(w, axis=0).astype(int).tolist())
+print("  per CTA: max over warps median %.0f, median over warps median %.0f" % (np.median(w.max(axis=1)), np.median(np.median(w, axis=1))))
 g0, g1 = tr[:, 0], tr[:, 14]
 print("step 6: first start -> last end %.2f us; gap from step 5 last end to step 6 first start %.2f us" % ((g1.max() - g0.min()) / 1e3, (g0.min() - tr5[:, 14].max()) / 1e3))
