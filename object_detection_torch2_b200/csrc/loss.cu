@@ -69,8 +69,9 @@ struct LossParams {
 };
 
 constexpr int kTracePoints = 64;
-__device__ __forceinline__ void trace_point(const LossParams& p, int idx) {
-  if (p.trace != nullptr && threadIdx.x == 0) {
+template <bool kTrace>
+__device__ __forceinline__ void trace_point_t(const LossParams& p, int idx) {
+  if (kTrace && p.trace != nullptr && threadIdx.x == 0) {
     unsigned long long t;
     if (idx == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     else t = clock64();
@@ -251,7 +252,7 @@ __device__ __forceinline__ void hist_add(uint32_t* hist_set0, bool active, int s
     atomicAdd(hist_set0 + set * 128 + (bin >> 1), static_cast<uint32_t>(__popc(peers)) << (16 * (bin & 1u)));
 }
 
-template <int kC, int kLossThreads, int kCluster>
+template <int kC, int kLossThreads, int kCluster, bool kTrace>
 __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const LossParams p) {
   constexpr int kLossWarps = kLossThreads / 32;
   cg::cluster_group cluster = cg::this_cluster();
@@ -284,8 +285,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // ---- setup ------------------------------------------------------------------------------------
-  trace_point(p, 0);
-  trace_point(p, 1);
+  trace_point_t<kTrace>(p, 0);
+  trace_point_t<kTrace>(p, 1);
   float4 pri[kSlots];
   bool valid[kSlots];
 #pragma unroll
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
 #pragma unroll
   for (int s = 0; s < kSlots; ++s) d[s] = make_corners(pri[s].x, pri[s].y, pri[s].z, pri[s].w);
 
-  trace_point(p, 2);
+  trace_point_t<kTrace>(p, 2);
   // ---- matching: bit g of (mhi:mlo)[s] = IoU(gt g, prior) > thr   (ssd.py:231-250) ----------------------------
   // Dense pass over the fast rows, branch-free and division-free.  e = inter - union * thr is one FMA, so its sign
   // is exact; |e| > union * thr * 2^-20 then decides fl(inter / union) > thr with certainty either way.  The
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       }
     }
   }
-  trace_point(p, 3);
+  trace_point_t<kTrace>(p, 3);
 
   // ---- per-row terms ----------------------------------------------------------------------------------
   // ce: positive CE (matched rows) or negative CE (unmatched rows); lloc: smooth-L1 sum; lse: log-sum-exp.
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     ce[s] = 0.0f; lloc[s] = 0.0f; lse[s] = 0.0f;
     if (s * kBlockRows >= my_rows_w) continue;                      // uniform per warp
     if (p.bulk && s == 0) mbar_wait(&sh.mbar[0][warp], 0);          // the whole chunk lands on one barrier
-    if (s == 0) trace_point(p, 4);
+    if (s == 0) trace_point_t<kTrace>(p, 4);
     float* rp = my_slab + static_cast<size_t>(s * kBlockRows + lane) * row;
     if (valid[s]) {
       float mx, sum = 0.0f;
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     if (lane == 0 && c) atomicAdd(&sh.pos_local, c);
   }
 
-  if (p.trace != nullptr && lane == 0) p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 24 + warp] = clock64();   // per-warp end of the row phase
+  if (kTrace && p.trace != nullptr && lane == 0) p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 24 + warp] = clock64();   // per-warp end of the row phase
 
   // ---- software pipelining across micro-batches: HBM goes quiet from here until the gradient leaves, so every
   // warp now asks the L2 for the same blocks of the NEXT batch (this SM will read them again in the next launch) ------
@@ -548,9 +549,9 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   }
 
   // ---- cluster exchange #1: positives + bucket histograms of both sets -----------------------------------------
-  trace_point(p, 5);
+  trace_point_t<kTrace>(p, 5);
   cluster.sync();
-  trace_point(p, 6);
+  trace_point_t<kTrace>(p, 6);
   if (tid < 256) {
     const int set = tid >> 7, w = tid & 127;
     uint32_t t = 0;
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   // The local radix passes reuse hist[1][*] (never touched outside the fallback) and tot[*] as their four zeroed
   // histograms; tot is free from here on (the cluster barrier below orders this clear before its reuse).
   if (tid < 256) (&sh.tot[0][0])[tid] = 0u;
-  trace_point(p, 7);
+  trace_point_t<kTrace>(p, 7);
 
   const int sel_set = sh.sel_set;
   const bool need_select = sh.need_select != 0;
@@ -608,9 +609,9 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       const int pos = base + __popc(ballot & lt_mask);
       if (member && pos < kListCap) sh.list[pos] = key;
     }
-    trace_point(p, 16);
+    trace_point_t<kTrace>(p, 16);
     cluster.sync();
-    trace_point(p, 17);
+    trace_point_t<kTrace>(p, 17);
     // everyone gathers every CTA's candidates and finishes the order statistic locally
     int cnt[kCluster], total = 0;
     bool over = false;
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
         sh.gathered[i] = cluster.map_shared_rank(&sh.list[0], r)[off];
       }
       __syncthreads();
-      trace_point(p, 18);
+      trace_point_t<kTrace>(p, 18);
       if (total <= 256) {
         // few candidates (the usual case): exact order statistic by counting, spread over the whole CTA.  With
         // above(v) = #{candidates > v}, the (rem+1)-th largest is the SMALLEST key whose above() is <= rem.  Thread t
@@ -717,7 +718,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     if (tid == 0) sh.overflow = over;
   }
   cluster.barrier_arrive();     // last access to distributed shared memory is behind us; the matching wait is at kernel end
-  trace_point(p, 8);
+  trace_point_t<kTrace>(p, 8);
   const float thr_sel = need_select ? key_float(sel_key) : 0.0f;
   const float thr_pos = sel_set == 0 ? thr_sel : 0.0f;
   const float thr_neg = sel_set == 1 ? thr_sel : 0.0f;
@@ -788,7 +789,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       }
     }
   }
-  trace_point(p, 9);
+  trace_point_t<kTrace>(p, 9);
   // ---- gradient rows, in place over the slab, then out by TMA -------------------------------------------------
   if (p.grad != nullptr) {
     const float sn = inv_pos * p.inv_n_global;          // d loss / d (per-image sum)
@@ -859,12 +860,12 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     }
   }
 
-  trace_point(p, 10);
+  trace_point_t<kTrace>(p, 10);
   if (p.bulk && p.grad != nullptr && lane == 0) bulk_store_wait();
   cluster.barrier_wait();       // my shared memory may be read by cluster peers until they have all passed their selection
-  trace_point(p, 11);
-  trace_point(p, 12);
-  if (p.trace != nullptr && tid == 0) {
+  trace_point_t<kTrace>(p, 11);
+  trace_point_t<kTrace>(p, 12);
+  if (kTrace && p.trace != nullptr && tid == 0) {
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 13] = smid;
@@ -909,9 +910,9 @@ static bool pick_shape(int P, int C, int G, LossShape* out) {
   return false;
 }
 
-template <int kC, int kT, int kCl>
+template <int kC, int kT, int kCl, bool kTrace>
 static int launch_loss(const LossParams& p, size_t smem, cudaStream_t st) {
-  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<kC, kT, kCl>), static_cast<int>(kMaxDynSmem), "ssdh_multibox_loss")) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<kC, kT, kCl, kTrace>), static_cast<int>(kMaxDynSmem), "ssdh_multibox_loss")) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(p.N) * kCl);
   cfg.blockDim = dim3(kT);
@@ -927,15 +928,21 @@ static int launch_loss(const LossParams& p, size_t smem, cudaStream_t st) {
   cfg.attrs = attr;
   static const int pdl = [] { const char* e = getenv("SSDH_LOSS_PDL"); return e ? atoi(e) : 1; }();
   cfg.numAttrs = pdl ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, multibox_loss_kernel<kC, kT, kCl>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, multibox_loss_kernel<kC, kT, kCl, kTrace>, p);
   if (e != cudaSuccess) { set_error("ssdh_multibox_loss: launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
   return 0;
 }
 
 template <int kC>
 static int launch_loss_shape(const LossParams& p, const LossShape& s, cudaStream_t st) {
-  if (s.cluster == 4) return launch_loss<kC, 768, 4>(p, s.smem, st);
-  return launch_loss<kC, 384, 8>(p, s.smem, st);
+  // the instrumented build of the kernel (debug hook, see the bottom of this file) is a separate instantiation: the
+  // production kernel carries no trace code at all
+  if (p.trace != nullptr) {
+    if (s.cluster == 4) return launch_loss<kC, 768, 4, true>(p, s.smem, st);
+    return launch_loss<kC, 384, 8, true>(p, s.smem, st);
+  }
+  if (s.cluster == 4) return launch_loss<kC, 768, 4, false>(p, s.smem, st);
+  return launch_loss<kC, 384, 8, false>(p, s.smem, st);
 }
 
 }  // namespace ssdh
@@ -1028,11 +1035,11 @@ extern "C" int ssdh_device_info(int* sm_count, int* max_smem_optin, int* loss_cl
     cfg.attrs = attr; cfg.numAttrs = 1;
     int nc = 0;
     if (shape.cluster == 4) {
-      ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<21, 768, 4>), static_cast<int>(kMaxDynSmem), "ssdh_device_info");
-      e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 768, 4>, &cfg);
+      ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<21, 768, 4, false>), static_cast<int>(kMaxDynSmem), "ssdh_device_info");
+      e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 768, 4, false>, &cfg);
     } else {
-      ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<21, 384, 8>), static_cast<int>(kMaxDynSmem), "ssdh_device_info");
-      e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 384, 8>, &cfg);
+      ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<21, 384, 8, false>), static_cast<int>(kMaxDynSmem), "ssdh_device_info");
+      e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 384, 8, false>, &cfg);
     }
     if (e != cudaSuccess) { set_error("ssdh_device_info: occupancy: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
     *loss_max_active_clusters = nc;
