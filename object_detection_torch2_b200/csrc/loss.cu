@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     __syncwarp();
   } else {
     const float* src = img_in + static_cast<size_t>(my_chunk) * kChunkRows * row;
+#pragma unroll 1
     for (int i = lane; i < my_rows_w * row; i += 32) my_slab[i] = src[i];
     __syncwarp();
   }
@@ -501,7 +502,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
             } else {
               const float* tw = p.targets + (static_cast<size_t>(n) * G + g) * row + 4;
               float dot = 0.0f;
-              for (int c = 0; c < C; ++c) dot += tw[c] * ((rp[4 + c] - mx) - ls);
+#pragma unroll 1
+              for (int c = 0; c < C; ++c) dot += tw[c] * ((rp[4 + c] - mx) - ls);      // soft labels: rare, kept small
               acc_ce += -dot;
             }
             const float x0 = l0 - (r.cx - q.x) * rdw;                // l - g-hat (ssd.py:202-204, 267-270)
@@ -746,27 +748,31 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     cnt2 = warp_sum(cnt2);
     if (lane == 0) { sh.wred_loss[warp] = acc; sh.wred_a[warp] = cnt2; }
     __syncthreads();
-    if (warp == 0) {
+    if (warp == kLossWarps - 1) {            // the warp with the least row work (none at all for P = 8732): the global
+                                             // round trips below stay off the other warps' gradient rows
       double t = lane < kLossWarps ? sh.wred_loss[lane] : 0.0;
       int c2 = lane < kLossWarps ? sh.wred_a[lane] : 0;
       t = warp_sum(t);                      // fixed shuffle tree: deterministic
       c2 = warp_sum(c2);
+      ImageSlot* slot = p.slots + n;
+      unsigned int arrived = 0u;
       if (lane == 0) {
-        ImageSlot* slot = p.slots + n;
         slot->part_loss[rank] = t;
         slot->part_sel[rank] = c2;
         __threadfence();
-        const unsigned int arrived = atomicAdd(&slot->ticket, 1u);
-        if (arrived == static_cast<unsigned int>(kCluster) - 1u) {
-          __threadfence();
-          double total = 0.0;
-          int pos_sel = 0, neg_sel = 0;
-          for (int r = 0; r < kCluster; ++r) {
-            total += __ldcg(&slot->part_loss[r]);
-            const int c = __ldcg(&slot->part_sel[r]);
-            pos_sel += c & 0xffff;
-            neg_sel += c >> 16;
-          }
+        arrived = atomicAdd(&slot->ticket, 1u);
+      }
+      arrived = __shfl_sync(0xffffffffu, arrived, 0);
+      if (arrived == static_cast<unsigned int>(kCluster) - 1u) {       // last CTA of the image: the whole warp helps
+        __threadfence();
+        const double pl = lane < kCluster ? __ldcg(&slot->part_loss[lane]) : 0.0;
+        const int c = lane < kCluster ? __ldcg(&slot->part_sel[lane]) : 0;
+        double total = 0.0;
+#pragma unroll
+        for (int r = 0; r < kCluster; ++r) total += __shfl_sync(0xffffffffu, pl, r);      // rank order: deterministic
+        const int pos_sel = warp_sum(c & 0xffff), neg_sel = warp_sum(c >> 16);
+        unsigned int done = 0u;
+        if (lane == 0) {
           slot->ticket = 0u;
           const float li = static_cast<float>(total) * inv_pos;
           if (p.stats) {
@@ -777,12 +783,16 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
           }
           slot->image_loss = static_cast<double>(li);
           __threadfence();
-          const unsigned int done = atomicAdd(p.ticket, 1u);
-          if (done == static_cast<unsigned int>(p.N) - 1u) {
-            __threadfence();
-            double sum = 0.0;
-            for (int i = 0; i < p.N; ++i) sum += __ldcg(&p.slots[i].image_loss);      // fixed order -> deterministic
-            *p.loss = static_cast<float>(sum * static_cast<double>(p.inv_n_global));
+          done = atomicAdd(p.ticket, 1u);
+        }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done == static_cast<unsigned int>(p.N) - 1u) {               // last image of the batch
+          __threadfence();
+          double acc = 0.0;                 // lane l adds images l, l + 32, ... in order, then a fixed shuffle tree
+          for (int i = lane; i < p.N; i += 32) acc += __ldcg(&p.slots[i].image_loss);
+          acc = warp_sum(acc);
+          if (lane == 0) {
+            *p.loss = static_cast<float>(acc * static_cast<double>(p.inv_n_global));
             *p.ticket = 0u;
           }
         }
@@ -814,6 +824,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
             tsum = 0.0f;
             for (int half = 0; half < 2; ++half) {
               uint32_t m = half ? mhi[s] : mlo[s];
+#pragma unroll 1
               while (m) { tsum += gts[32 * half + __ffs(m) - 1].tsum; m &= m - 1; }
             }
           }
@@ -836,7 +847,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
                   rp[4 + label] -= sn;
                 } else {
                   const float* tw = p.targets + (static_cast<size_t>(n) * G + g) * row + 4;
-                  for (int c = 0; c < C; ++c) rp[4 + c] -= sn * tw[c];
+#pragma unroll 1
+                  for (int c = 0; c < C; ++c) rp[4 + c] -= sn * tw[c];      // soft labels: rare, kept small
                 }
               }
             }
@@ -855,6 +867,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
         }
       } else {
         __syncwarp();
+#pragma unroll 1
         for (int i = lane; i < rows_b * row; i += 32) dst[i] = srcb[i];
       }
     }
