@@ -517,6 +517,7 @@ struct SmallShared {
 #define NMS_TRACE(idx) do { if (p.trace != nullptr && threadIdx.x == 0) p.trace[static_cast<size_t>(blockIdx.x) * 16 + (idx)] = clock64(); } while (0)
 static unsigned long long* g_nms_trace = nullptr;
 
+template <bool kPerClass>
 __global__ void __launch_bounds__(kSmallThreads, 3) nms_small_kernel(const NmsParams p, int32_t* __restrict__ large) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmallShared& sh = *reinterpret_cast<SmallShared*>(smem_raw);
@@ -646,6 +647,7 @@ __global__ void __launch_bounds__(kSmallThreads, 3) nms_small_kernel(const NmsPa
 
   NMS_TRACE(2);
   // ---- sorted candidates: order list, boxes ---------------------------------------------------------------------
+  bool odd_box = false;            // an area that is not a normal positive number: the whole image takes the exact path
   if (tid < K) {
     const int r = sh.idx[cur][tid];
     order[tid] = r;
@@ -653,9 +655,15 @@ __global__ void __launch_bounds__(kSmallThreads, 3) nms_small_kernel(const NmsPa
     const Corners c = make_corners(b[0], b[1], b[2], b[3]);
     sh.box[tid] = make_float4(c.x1, c.x2, c.y1, c.y2);
     sh.area[tid] = c.area;
-    sh.cls[tid] = p.per_class ? cls_in[r] : 0;
+    sh.cls[tid] = kPerClass ? cls_in[r] : 0;
+    odd_box = !(c.area >= 1e-30f && c.area <= 1e30f);
+  } else if (tid < ((K + 31) & ~31)) {
+    // padding up to a full word of columns: an empty box far away never overlaps anything (and is never ambiguous)
+    sh.box[tid] = make_float4(3e38f, 3e38f, 3e38f, 3e38f);
+    sh.area[tid] = 1.0f;
+    sh.cls[tid] = -1;
   }
-  __syncthreads();
+  const bool all_tame = __syncthreads_and(!odd_box) != 0;
 
   NMS_TRACE(3);
   // ---- C1. overlaps: warp per row i, lane per later column j; the (sparse) hits are recorded at the SUPPRESSED side,
@@ -663,33 +671,46 @@ __global__ void __launch_bounds__(kSmallThreads, 3) nms_small_kernel(const NmsPa
   const ThrBand band = p.band;
   const PairThr pt = make_pair_thr(band.thr);
   const int Kw = (K + 31) / 32;
+  const bool fast_ok = pt.usable && all_tame;      // then union >= max(area) > 0 and only |e| <= m is ambiguous
   for (int i = warp; i < K; i += kSmallWarps) {
     const float4 bi = sh.box[i];
     const float ai = sh.area[i];
     const int ci = sh.cls[i];
     const uint32_t ibit = 1u << (i & 31);
-    bool row_amb = !pt.usable;
-    for (int w = i >> 5; w < Kw; ++w) {
-      const int jj = 32 * w + lane;
-      const int j = min(jj, K - 1);
-      bool amb;
-      bool hit = pair_hit_fast(bi, ai, sh.box[j], sh.area[j], pt, amb);
-      row_amb |= amb;
-      if (p.per_class) hit = hit && sh.cls[j] == ci;
-      if (hit && jj > i && jj < K) atomicOr(&sh.ov_in[jj][i >> 5], ibit);
+    const int w0 = i >> 5;
+    bool row_amb = !fast_ok;
+    if (fast_ok) {
+      // columns are padded to whole words with inert boxes, so the only bound to respect is j > i in the first word
+      float slack = 1.0f;                              // min over pairs of |e| - m; <= 0: some pair sits in the band
+      auto pair = [&](int w, bool allowed) {
+        const int j = 32 * w + lane;
+        const float4 bj = sh.box[j];
+        const float wd = fmaxf(fminf(bi.y, bj.y) - fmaxf(bi.x, bj.x), 0.0f);
+        const float ht = fmaxf(fminf(bi.w, bj.w) - fmaxf(bi.z, bj.z), 0.0f);
+        const float inter = wd * ht;
+        const float uni = (ai + sh.area[j]) - inter;
+        const float e = fmaf(uni, pt.nthr, inter), m = uni * pt.eps;
+        slack = fminf(slack, fabsf(e) - m);
+        bool hit = allowed && e > m;
+        if (kPerClass) hit = hit && sh.cls[j] == ci;
+        if (hit) atomicOr(&sh.ov_in[j][w0], ibit);
+      };
+      pair(w0, lane > (i & 31));
+      for (int w = w0 + 1; w < Kw; ++w) pair(w, true);
+      row_amb = !(slack > 0.0f);
     }
     if (__any_sync(0xffffffffu, row_amb)) {          // rare: redo the row with the exact division (set or clear each bit)
       Corners a;
       a.x1 = bi.x; a.x2 = bi.y; a.y1 = bi.z; a.y2 = bi.w; a.area = ai;
-      for (int w = i >> 5; w < Kw; ++w) {
+      for (int w = w0; w < Kw; ++w) {
         const int jj = 32 * w + lane;
         if (jj > i && jj < K) {
           const float4 bj = sh.box[jj];
           Corners o;
           o.x1 = bj.x; o.x2 = bj.y; o.y1 = bj.z; o.y2 = bj.w; o.area = sh.area[jj];
           const bool hit = iou_gt(a, o, band) && (sh.cls[jj] == ci);
-          if (hit) atomicOr(&sh.ov_in[jj][i >> 5], ibit);
-          else atomicAnd(&sh.ov_in[jj][i >> 5], ~ibit);
+          if (hit) atomicOr(&sh.ov_in[jj][w0], ibit);
+          else atomicAnd(&sh.ov_in[jj][w0], ~ibit);
         }
       }
     }
@@ -859,7 +880,8 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   const int row = 4 + C;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_score_kernel), 96 * 1024, fn)) return e;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel), 227 * 1024, fn)) return e;
-  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel), 100 * 1024, fn)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel<false>), 100 * 1024, fn)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel<true>), 100 * 1024, fn)) return e;
   NmsParams p;
   p.outputs = outputs; p.P = P; p.C = C;
   p.cand_key = w.cand_key; p.cand_cls = w.cand_cls;
@@ -918,7 +940,8 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
       pk.order = p.order + off; pk.keep = p.keep + off;
       pk.order_cnt = p.order_cnt ? p.order_cnt + n0 : nullptr;
       pk.keep_cnt = p.keep_cnt ? p.keep_cnt + n0 : nullptr;
-      if (int e = launch(nms_small_kernel, static_cast<unsigned>(nk), kSmallThreads, small_smem, true, pk, w.large + n0)) return e;
+      if (int e = per_class ? launch(nms_small_kernel<true>, static_cast<unsigned>(nk), kSmallThreads, small_smem, true, pk, w.large + n0)
+                            : launch(nms_small_kernel<false>, static_cast<unsigned>(nk), kSmallThreads, small_smem, true, pk, w.large + n0)) return e;
     }
   }
   return launch(nms_kernel, static_cast<unsigned>(N), kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
