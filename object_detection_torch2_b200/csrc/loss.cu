@@ -151,6 +151,19 @@ __device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src,
 }
 __device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// Cluster barrier for data that lives in the WRITER's own shared memory (histograms, candidate lists, counters) and is
+// read by the peers through distributed shared memory afterwards.  cooperative groups' cluster.sync() arrives with
+// .release at cluster scope, which this chip implements as MEMBAR.ALL.GPU (+ ERRBAR / CGAERRBAR): it drains every
+// outstanding memory operation of the SM, ~0.5 k cycles with TMA traffic in flight.  For writes to one's own shared
+// memory a CTA-scope fence is enough -- once MEMBAR.ALL.CTA has retired they ARE in the SM's shared memory, which is
+// where a peer's remote load looks (the same reliance CUTLASS places on mbarrier.init + cluster_arrive_relaxed).
+__device__ __forceinline__ void cluster_arrive_own_smem() {
+  __syncwarp();
+  asm volatile("fence.acq_rel.cta;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_arrive_nodata() { __syncwarp(); asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { __syncwarp(); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Packed fp32 pairs (FFMA2 / FADD2 on sm_100a): one issue slot for two lanes of the class loop.
@@ -552,7 +565,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
 
   // ---- cluster exchange #1: positives + bucket histograms of both sets -----------------------------------------
   trace_point_t<kTrace>(p, 5);
-  cluster.sync();
+  cluster_arrive_own_smem();
+  cluster_wait_acquire();
   trace_point_t<kTrace>(p, 6);
   if (tid < 256) {
     const int set = tid >> 7, w = tid & 127;
@@ -612,7 +626,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       if (member && pos < kListCap) sh.list[pos] = key;
     }
     trace_point_t<kTrace>(p, 16);
-    cluster.sync();
+    cluster_arrive_own_smem();
+    cluster_wait_acquire();
     trace_point_t<kTrace>(p, 17);
     // everyone gathers every CTA's candidates and finishes the order statistic locally
     int cnt[kCluster], total = 0;
@@ -719,7 +734,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     sel_key = prefix;
     if (tid == 0) sh.overflow = over;
   }
-  cluster.barrier_arrive();     // last access to distributed shared memory is behind us; the matching wait is at kernel end
+  cluster_arrive_nodata();      // last access to distributed shared memory is behind us; the matching wait is at kernel end
   trace_point_t<kTrace>(p, 8);
   const float thr_sel = need_select ? key_float(sel_key) : 0.0f;
   const float thr_pos = sel_set == 0 ? thr_sel : 0.0f;
@@ -875,7 +890,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
 
   trace_point_t<kTrace>(p, 10);
   if (p.bulk && p.grad != nullptr && lane == 0) bulk_store_wait();
-  cluster.barrier_wait();       // my shared memory may be read by cluster peers until they have all passed their selection
+  cluster_wait_acquire();       // my shared memory may be read by cluster peers until they have all passed their selection
   trace_point_t<kTrace>(p, 11);
   trace_point_t<kTrace>(p, 12);
   if (kTrace && p.trace != nullptr && tid == 0) {
