@@ -322,6 +322,29 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   float gt_first = 0.0f;
   if (warp < G) gt_first = __ldg(p.targets + (static_cast<size_t>(n) * G + warp) * row + min(lane, row - 1));
 
+  // ---- while the ground truth is on its way: corners of my priors and the outer bounds of my whole chunk (box around
+  // its priors, smallest / largest prior area), used below to drop ground-truth rows that cannot match ANY of them -----
+  Corners d[kSlots];
+  float cb_x1 = 3e38f, cb_x2 = -3e38f, cb_y1 = 3e38f, cb_y2 = -3e38f, cb_amin = 3e38f, cb_amax = -3e38f;
+  bool tame = true;                        // every prior of the chunk has finite positive width and height
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    d[s] = make_corners(pri[s].x, pri[s].y, pri[s].z, pri[s].w);
+    if (valid[s]) {
+      cb_x1 = fminf(cb_x1, d[s].x1); cb_x2 = fmaxf(cb_x2, d[s].x2);
+      cb_y1 = fminf(cb_y1, d[s].y1); cb_y2 = fmaxf(cb_y2, d[s].y2);
+      cb_amin = fminf(cb_amin, d[s].area); cb_amax = fmaxf(cb_amax, d[s].area);
+      tame = tame && pri[s].z > 0.0f && pri[s].w > 0.0f && pri[s].z < 1e18f && pri[s].w < 1e18f && fabsf(pri[s].x) < 1e18f && fabsf(pri[s].y) < 1e18f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cb_x1 = fminf(cb_x1, __shfl_xor_sync(0xffffffffu, cb_x1, o)); cb_x2 = fmaxf(cb_x2, __shfl_xor_sync(0xffffffffu, cb_x2, o));
+    cb_y1 = fminf(cb_y1, __shfl_xor_sync(0xffffffffu, cb_y1, o)); cb_y2 = fmaxf(cb_y2, __shfl_xor_sync(0xffffffffu, cb_y2, o));
+    cb_amin = fminf(cb_amin, __shfl_xor_sync(0xffffffffu, cb_amin, o)); cb_amax = fmaxf(cb_amax, __shfl_xor_sync(0xffffffffu, cb_amax, o));
+  }
+  tame = __all_sync(0xffffffffu, tame);
+
   // ---- ground truth of this image -> shared: one warp per row, one coalesced request each -----------------
   for (int g = warp; g < G; g += kLossWarps) {
     const float* tr = p.targets + (static_cast<size_t>(n) * G + g) * row;
@@ -382,10 +405,6 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     __syncwarp();
   }
 
-  Corners d[kSlots];
-#pragma unroll
-  for (int s = 0; s < kSlots; ++s) d[s] = make_corners(pri[s].x, pri[s].y, pri[s].z, pri[s].w);
-
   trace_point_t<kTrace>(p, 2);
   // ---- matching: bit g of (mhi:mlo)[s] = IoU(gt g, prior) > thr   (ssd.py:231-250) ----------------------------
   // Dense pass over the fast rows, branch-free and division-free.  e = inter - union * thr is one FMA, so its sign
@@ -400,9 +419,35 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     const ThrBand band = p.band;
     const float nthr = -band.thr, eps = band.thr * 9.5367431640625e-07f;
     const int n_fast = sh.n_fast, n_slow = sh.n_slow;
+    // Cull: lane i looks at fast row i (and i + 32).  IoU > thr needs inter * (1 + thr) > thr * (area_g + area_p), and
+    // inter can exceed neither the overlap of the row with the chunk's outer box nor either area; a row that fails this
+    // bound (with a 1e-4 safety margin, far above any rounding) for the chunk's extreme areas matches none of my priors.
+    uint32_t keep_lo = 0u, keep_hi = 0u;
+    {
+      const float thr = band.thr;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1 && n_fast <= 32) break;            // uniform
+        const int i = 32 * half + lane;
+        const bool have = i < n_fast;
+        const int g = have ? sh.gt_fast[i] : 0;
+        const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
+        const float garea = gts[g].area;
+        const float w = fmaxf(fminf(q.y, cb_x2) - fmaxf(q.x, cb_x1), 0.0f);
+        const float h = fmaxf(fminf(q.w, cb_y2) - fmaxf(q.z, cb_y1), 0.0f);
+        const float imax = fminf(fminf(w * h, cb_amax), garea);
+        const bool hopeless = imax * (1.0f + thr) <= thr * (garea + cb_amin) * 0.9999f;
+        const uint32_t k = __ballot_sync(0xffffffffu, have && !(tame && hopeless));
+        if (half == 0) keep_lo = k; else keep_hi = k;
+      }
+    }
     float amb = 1.0f;                              // min over pairs of |e| - margin; <= 0 means "settle exactly"
+    const int n_keep = __popc(keep_lo) + __popc(keep_hi);
 #pragma unroll 2
-    for (int i = 0; i < n_fast; ++i) {
+    for (int it = 0; it < n_keep; ++it) {
+      int i;
+      if (keep_lo) { i = __ffs(keep_lo) - 1; keep_lo &= keep_lo - 1; }
+      else { i = 32 + __ffs(keep_hi) - 1; keep_hi &= keep_hi - 1; }
       const int g = sh.gt_fast[i];
       const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
       const float garea = gts[g].area;
