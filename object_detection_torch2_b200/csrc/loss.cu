@@ -322,28 +322,26 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   float gt_first = 0.0f;
   if (warp < G) gt_first = __ldg(p.targets + (static_cast<size_t>(n) * G + warp) * row + min(lane, row - 1));
 
-  // ---- while the ground truth is on its way: corners of my priors and the outer bounds of my whole chunk (box around
-  // its priors, smallest / largest prior area), used below to drop ground-truth rows that cannot match ANY of them -----
-  Corners d[kSlots];
-  float cb_x1 = 3e38f, cb_x2 = -3e38f, cb_y1 = 3e38f, cb_y2 = -3e38f, cb_amin = 3e38f, cb_amax = -3e38f;
-  bool tame = true;                        // every prior of the chunk has finite positive width and height
-#pragma unroll
-  for (int s = 0; s < kSlots; ++s) {
-    d[s] = make_corners(pri[s].x, pri[s].y, pri[s].z, pri[s].w);
-    if (valid[s]) {
-      cb_x1 = fminf(cb_x1, d[s].x1); cb_x2 = fmaxf(cb_x2, d[s].x2);
-      cb_y1 = fminf(cb_y1, d[s].y1); cb_y2 = fmaxf(cb_y2, d[s].y2);
-      cb_amin = fminf(cb_amin, d[s].area); cb_amax = fmaxf(cb_amax, d[s].area);
-      tame = tame && pri[s].z > 0.0f && pri[s].w > 0.0f && pri[s].z < 1e18f && pri[s].w < 1e18f && fabsf(pri[s].x) < 1e18f && fabsf(pri[s].y) < 1e18f;
+  // ---- slab: every warp fetches its own 96-row chunk with ONE TMA bulk copy onto its own mbarrier; issued right
+  // behind the (tiny) ground-truth request, so that it lands while the ground truth is being unpacked -----------------
+  float* my_slab = slab + static_cast<size_t>(warp) * kChunkRows * row;
+  if (p.bulk) {
+    if (lane == 0) {
+      mbar_init(&sh.mbar[0][warp], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (my_rows_w > 0) {
+        const uint32_t bytes = static_cast<uint32_t>(my_rows_w) * row * sizeof(float);
+        mbar_expect_tx(&sh.mbar[0][warp], bytes);
+        bulk_load_hint(my_slab, img_in + static_cast<size_t>(my_chunk) * kChunkRows * row, bytes, &sh.mbar[0][warp], policy_evict_first());
+      }
     }
+    __syncwarp();
+  } else {
+    const float* src = img_in + static_cast<size_t>(my_chunk) * kChunkRows * row;
+#pragma unroll 1
+    for (int i = lane; i < my_rows_w * row; i += 32) my_slab[i] = src[i];
+    __syncwarp();
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    cb_x1 = fminf(cb_x1, __shfl_xor_sync(0xffffffffu, cb_x1, o)); cb_x2 = fmaxf(cb_x2, __shfl_xor_sync(0xffffffffu, cb_x2, o));
-    cb_y1 = fminf(cb_y1, __shfl_xor_sync(0xffffffffu, cb_y1, o)); cb_y2 = fmaxf(cb_y2, __shfl_xor_sync(0xffffffffu, cb_y2, o));
-    cb_amin = fminf(cb_amin, __shfl_xor_sync(0xffffffffu, cb_amin, o)); cb_amax = fmaxf(cb_amax, __shfl_xor_sync(0xffffffffu, cb_amax, o));
-  }
-  tame = __all_sync(0xffffffffu, tame);
 
   // ---- ground truth of this image -> shared: one warp per row, one coalesced request each -----------------
   for (int g = warp; g < G; g += kLossWarps) {
@@ -382,28 +380,30 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       if (r.label < 0 && c.area > 0.0f) sh.soft_labels = 1;
     }
   }
-  __syncthreads();
-
-  // ---- slab: every warp fetches its own 96-row chunk with ONE TMA bulk copy onto its own mbarrier; issued only now,
-  // after the ground truth landed, so the small loads were never queued behind this traffic ---------------------------
-  float* my_slab = slab + static_cast<size_t>(warp) * kChunkRows * row;
-  if (p.bulk) {
-    if (lane == 0) {
-      mbar_init(&sh.mbar[0][warp], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      if (my_rows_w > 0) {
-        const uint32_t bytes = static_cast<uint32_t>(my_rows_w) * row * sizeof(float);
-        mbar_expect_tx(&sh.mbar[0][warp], bytes);
-        bulk_load_hint(my_slab, img_in + static_cast<size_t>(my_chunk) * kChunkRows * row, bytes, &sh.mbar[0][warp], policy_evict_first());
-      }
+    // ---- corners of my priors and the outer bounds of my whole chunk (box around its priors, smallest / largest prior
+  // area), used below to drop ground-truth rows that cannot match ANY of them ------------------------------------
+  Corners d[kSlots];
+  float cb_x1 = 3e38f, cb_x2 = -3e38f, cb_y1 = 3e38f, cb_y2 = -3e38f, cb_amin = 3e38f, cb_amax = -3e38f;
+  bool tame = true;                        // every prior of the chunk has finite positive width and height
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    d[s] = make_corners(pri[s].x, pri[s].y, pri[s].z, pri[s].w);
+    if (valid[s]) {
+      cb_x1 = fminf(cb_x1, d[s].x1); cb_x2 = fmaxf(cb_x2, d[s].x2);
+      cb_y1 = fminf(cb_y1, d[s].y1); cb_y2 = fmaxf(cb_y2, d[s].y2);
+      cb_amin = fminf(cb_amin, d[s].area); cb_amax = fmaxf(cb_amax, d[s].area);
+      tame = tame && pri[s].z > 0.0f && pri[s].w > 0.0f && pri[s].z < 1e18f && pri[s].w < 1e18f && fabsf(pri[s].x) < 1e18f && fabsf(pri[s].y) < 1e18f;
     }
-    __syncwarp();
-  } else {
-    const float* src = img_in + static_cast<size_t>(my_chunk) * kChunkRows * row;
-#pragma unroll 1
-    for (int i = lane; i < my_rows_w * row; i += 32) my_slab[i] = src[i];
-    __syncwarp();
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cb_x1 = fminf(cb_x1, __shfl_xor_sync(0xffffffffu, cb_x1, o)); cb_x2 = fmaxf(cb_x2, __shfl_xor_sync(0xffffffffu, cb_x2, o));
+    cb_y1 = fminf(cb_y1, __shfl_xor_sync(0xffffffffu, cb_y1, o)); cb_y2 = fmaxf(cb_y2, __shfl_xor_sync(0xffffffffu, cb_y2, o));
+    cb_amin = fminf(cb_amin, __shfl_xor_sync(0xffffffffu, cb_amin, o)); cb_amax = fmaxf(cb_amax, __shfl_xor_sync(0xffffffffu, cb_amax, o));
+  }
+  tame = __all_sync(0xffffffffu, tame);
+
+  __syncthreads();
 
   trace_point_t<kTrace>(p, 2);
   // ---- matching: bit g of (mhi:mlo)[s] = IoU(gt g, prior) > thr   (ssd.py:231-250) ----------------------------
