@@ -79,13 +79,13 @@ __device__ __forceinline__ void trace_point_t(const LossParams& p, int idx) {
   }
 }
 
-struct GtRec {             // 48 bytes, one per ground-truth row of the image
-  float x1, x2, y1, y2;    // corners                      (ssd.py:247-248)
-  float area, cx, cy, lw;  // lw = log(w) (or w when w <= 0, ssd.py:269)
-  float lh;
-  int label;               // class index when the class vector is exactly one-hot, else -1
-  int flags;               // bit0: w > 0, bit1: h > 0
+struct GtRec {             // 48 bytes, one per ground-truth row of the image; three 16-byte groups = three loads
+  float x1, x2, y1, y2;    // corners                      (ssd.py:247-248)       -- matching
+  float cx, cy, lw, lh;    // lw = log(w) (or w when w <= 0, ssd.py:269)           -- offsets of a matched pair
+  float area;              //                                                     -- matching
   float tsum;              // sum of the class vector
+  int label;               // class index when the class vector is exactly one-hot, else -1   -- matched pair (with flags)
+  int flags;               // bit0: w > 0, bit1: h > 0
 };
 
 struct LossShared {
@@ -547,6 +547,9 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
         const float ldw = __logf(q.z), ldh = __logf(q.w);             // offsets only feed loss values: fast math is ample
         const float rdw = __frcp_rn(q.z), rdh = __frcp_rn(q.w);
         const float l0 = rp[0], l1 = rp[1], l2 = rp[2], l3 = rp[3];
+        // l - g-hat per matched row (ssd.py:202-204, 267-270) = (l + d_c / d_w) - g_c / d_w and (l + log d_w) - log g_w:
+        // the prior-only parts are hoisted, leaving one FMA / one add per coordinate and pair
+        const float a0 = fmaf(q.x, rdw, l0), a1 = fmaf(q.y, rdh, l1), b2 = l2 + ldw, b3 = l3 + ldh;
         float acc_ce = 0.0f, acc_loc = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -554,9 +557,10 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
           while (m) {
             const int g = 32 * half + __ffs(m) - 1;
             m &= m - 1;
-            const GtRec& r = gts[g];
-            if (r.label >= 0) {
-              acc_ce += ls - (rp[4 + r.label] - mx);                 // -log_softmax[label]  (ssd.py:208-209)
+            const float4 go = *reinterpret_cast<const float4*>(&gts[g].cx);      // cx, cy, lw, lh
+            const int2 lf = *reinterpret_cast<const int2*>(&gts[g].label);         // label, flags
+            if (lf.x >= 0) {
+              acc_ce += ls - (rp[4 + lf.x] - mx);                    // -log_softmax[label]  (ssd.py:208-209)
             } else {
               const float* tw = p.targets + (static_cast<size_t>(n) * G + g) * row + 4;
               float dot = 0.0f;
@@ -564,13 +568,16 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
               for (int c = 0; c < C; ++c) dot += tw[c] * ((rp[4 + c] - mx) - ls);      // soft labels: rare, kept small
               acc_ce += -dot;
             }
-            const float x0 = l0 - (r.cx - q.x) * rdw;                // l - g-hat (ssd.py:202-204, 267-270)
-            const float x1 = l1 - (r.cy - q.y) * rdh;
-            const float x2 = l2 - ((r.flags & 1) ? r.lw - ldw : r.lw);
-            const float x3 = l3 - ((r.flags & 2) ? r.lh - ldh : r.lh);
+            const float x0 = fmaf(-go.x, rdw, a0);
+            const float x1 = fmaf(-go.y, rdh, a1);
+            const float x2 = ((lf.y & 1) ? b2 : l2) - go.z;
+            const float x3 = ((lf.y & 2) ? b3 : l3) - go.w;
             // with c = clamp(x, -1, 1): smooth_l1(x) = c * (x - c / 2)  (ssd.py:283) and c is its derivative
             const float c0 = clamp1(x0), c1 = clamp1(x1), c2 = clamp1(x2), c3 = clamp1(x3);
-            acc_loc += (c0 * fmaf(-0.5f, c0, x0) + c1 * fmaf(-0.5f, c1, x1)) + (c2 * fmaf(-0.5f, c2, x2) + c3 * fmaf(-0.5f, c3, x3));
+            acc_loc = fmaf(c0, fmaf(-0.5f, c0, x0), acc_loc);
+            acc_loc = fmaf(c1, fmaf(-0.5f, c1, x1), acc_loc);
+            acc_loc = fmaf(c2, fmaf(-0.5f, c2, x2), acc_loc);
+            acc_loc = fmaf(c3, fmaf(-0.5f, c3, x3), acc_loc);
             g0 += c0; g1 += c1; g2 += c2; g3 += c3;
           }
         }
