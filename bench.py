@@ -34,6 +34,7 @@ P, C, ROW = 8732, 21, 25
 BATCH = 32                  # per GPU (configs[1])
 POST_BATCH = 256            # configs[2]
 ROT = 12                    # rotating buffer pairs: 12 x (27.9 + 27.9) MB = 671 MB >> 126 MB L2
+GRAPH_STEPS = 48            # steps per CUDA-graph replay (4 rotations): the hand-over between replays is not pipelined
 SLAB = P * ROW * 4          # 873 200 B per image
 
 
@@ -176,15 +177,15 @@ def main():
     outs = [o.to(dev) for o in outs]
     tgts = [t.to(dev).contiguous() for t in tgts]
     grads = [torch.empty_like(o) for o in outs]
-    losses = torch.zeros(ROT, dtype=torch.float32, device=dev)
+    losses = torch.zeros(GRAPH_STEPS, dtype=torch.float32, device=dev)
 
-    def step(i):
+    def step(k):
         # software pipelining: while batch i is on chip the kernel asks the L2 for batch i+1 (HBM is idle then)
-        nxt = (i + 1) % ROT
+        i, nxt = k % ROT, (k + 1) % ROT
         ops.multibox_loss_raw(outs[i], tgts[i], priors, a=1.0, threshold=0.25, n_global=n_global, want_grad=True,
-                              loss_out=losses[i], grad_out=grads[i], next_outputs=outs[nxt], next_targets=tgts[nxt])
+                              loss_out=losses[k], grad_out=grads[i], next_outputs=outs[nxt], next_targets=tgts[nxt])
 
-    # one CUDA graph = ROT consecutive steps (one per rotating buffer pair)
+    # one CUDA graph = GRAPH_STEPS consecutive steps cycling through the ROT buffer pairs
     cap = torch.cuda.Stream(device=dev)
     cap.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(cap):
@@ -192,15 +193,15 @@ def main():
             step(i)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=cap):
-            for i in range(ROT):
+            for i in range(GRAPH_STEPS):
                 step(i)
     torch.cuda.current_stream().wait_stream(cap)
     torch.cuda.synchronize()
 
-    replays = max(1, -(-args.steps // ROT))
-    steps = replays * ROT                      # exactly `steps` timed steps (rounded up to whole rotations)
-    warm_replays = max(1, -(-args.warmup // ROT))
-    reducer = parallel.ScalarAllReducer(width=ROT, window=1, device=dev, dtype=torch.float32)
+    replays = max(1, -(-args.steps // GRAPH_STEPS))
+    steps = replays * GRAPH_STEPS              # exactly `steps` timed steps (rounded up to whole replays)
+    warm_replays = max(1, -(-args.warmup // GRAPH_STEPS))
+    reducer = parallel.ScalarAllReducer(width=GRAPH_STEPS, window=1, device=dev, dtype=torch.float32)
 
     def run(n_replays):
         for _ in range(n_replays):
@@ -233,7 +234,7 @@ def main():
     elapsed_ms = float(elapsed_ms)
     ms_per_step = elapsed_ms / steps
     value = n_global * steps / (elapsed_ms * 1e-3)
-    loss_value = float(reduced[-1].sum()) / ROT if reduced is not None else float(losses.mean())
+    loss_value = float(reduced[-1].sum()) / GRAPH_STEPS if reduced is not None else float(losses.mean())
 
     # ---- roofline of the dominant (only) kernel of the step ----------------------------------------------------
     peak, peak_src = measured_peak()
@@ -290,12 +291,12 @@ def main():
            "loss_check": float(h_loss[-1])}
 
     line = {"metric": "images/s for SSD300 match+MultiBox loss (fwd+grad) training step", "value": value, "unit": "images/s",
-            "n_gpus": world, "steps": steps, "warmup": warm_replays * ROT, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "n_gpus": world, "steps": steps, "warmup": warm_replays * GRAPH_STEPS, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "SSD300 head training step: IoU match + MultiBox loss fwd+grad, batch 32 per GPU, G<=20, dist " + args.dist,
                        "global_batch": n_global, "priors": P, "classes": C, "gt_rows": G,
                        "l2": f"inputs larger than L2: rotation over {ROT} (outputs, grad) buffer pairs = {ROT * 2 * BATCH * SLAB / 1e6:.0f} MB",
-                       "launch": f"CUDA graph of {ROT} steps, C ABI ssdh_multibox_loss_pipelined (in-kernel L2 prefetch of the next batch, programmatic dependent launch between steps)", "parallelism": f"dp{world} (images sharded, scalar all-reduce per replay)"},
+                       "launch": f"CUDA graph of {GRAPH_STEPS} steps, C ABI ssdh_multibox_loss_pipelined (in-kernel L2 prefetch of the next batch, programmatic dependent launch between steps)", "parallelism": f"dp{world} (images sharded, scalar all-reduce per replay)"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": steps, "clocks": clocks, "loss": loss_value}
 
     if rank == 0 and world == 1 and not args.no_extras:
