@@ -476,7 +476,8 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
         }
       }
     }
-    const bool unsure = !(amb > 0.0f);
+    // the band argument needs a positive union: chunks holding a prior of non-positive or non-finite extent settle exactly
+    const bool unsure = !(amb > 0.0f) || !tame;
     if (__any_sync(0xffffffffu, unsure) || n_slow > 0) {
       const int n_exact = n_slow + (unsure ? n_fast : 0);
       for (int i = 0; i < n_exact; ++i) {          // exact path: borderline pairs, exotic rows / thresholds
