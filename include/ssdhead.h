@@ -119,6 +119,17 @@ SSDH_API int ssdh_multibox_loss_pipelined(const float* outputs, const float* tar
  * the SMs, changes no data; ptr must be 16-byte aligned. */
 SSDH_API int ssdh_prefetch_l2(const void* ptr, size_t bytes, ssdh_stream_t stream);
 
+/* SURVEY 8f-1 -- head-output producer, the tail of SSD.forward (src/model/ssd.py:96-104): the n_levels detector outputs
+ * levels[k] (N, ch[k], hw[k]) fp32 NCHW-contiguous, ch[k] = anchors_k * width, are written as
+ * permute(0, 2, 3, 1).reshape(N, -1, width) blocks, concatenated along dim 1, into outputs (N, P, width) in ONE pass
+ * (the reference makes seven copies).  levels / ch / hw are HOST arrays; P must equal sum_k hw[k] * ch[k] / width. */
+SSDH_API int ssdh_pack_head(const float* const* levels, const int* ch, const int* hw, int n_levels, int N, int width,
+                            float* outputs, int P, ssdh_stream_t stream);
+
+/* Backward of ssdh_pack_head: scatters grad_outputs (N, P, width) into the detectors' NCHW gradients level_grads[k]. */
+SSDH_API int ssdh_unpack_head(const float* grad_outputs, float* const* level_grads, const int* ch, const int* hw, int n_levels,
+                              int N, int width, int P, ssdh_stream_t stream);
+
 /* grad *= *scale (device scalar), skipped entirely when *scale == 1: the autograd chain-rule hook. */
 SSDH_API int ssdh_scale_inplace(float* x, size_t n, const float* scale, ssdh_stream_t stream);
 

@@ -1,0 +1,106 @@
+// head-output producer.  Replaces the tail of SSD.forward (reference src/model/ssd.py:96-104): every
+// detector output x_k (N, A_k * (4 + C), H_k, W_k) goes through permute(0, 2, 3, 1).reshape(N, -1, 4 + C) and the six
+// results are concatenated along dim 1 into (N, 8732, 4 + C) -- seven full copies of the data in the reference.
+//
+// Per (level, image) that is a plain 2-D transpose: the input is a [CH = A * (4 + C)] x [HW] matrix (HW contiguous), the
+// output block a [HW] x [CH] matrix (row (i * W + j) * A + a, column c  <->  channel a * (4 + C) + c at cell (i, j)),
+// stored at row offset off_k of the image's slab.  One launch moves all levels of all images through shared-memory tiles
+// of 32 cells x all channels: coalesced reads along HW, one contiguous block written per tile, every byte read once and
+// written once.  The same kernel run
+// backwards (kUnpack) scatters d loss / d outputs into the detectors' NCHW gradients for autograd.
+#include "common.cuh"
+
+namespace ssdh {
+
+constexpr int kPackMaxLevels = 8;
+constexpr int kTile = 32;
+
+struct PackParams {
+  float* level[kPackMaxLevels];      // NCHW tensors, (N, ch, hw) each
+  int ch[kPackMaxLevels], hw[kPackMaxLevels];
+  int row_off[kPackMaxLevels];       // first slab row of the level (in rows of `width` floats)
+  int tile_start[kPackMaxLevels + 1];   // prefix sum of tiles (32 cells each) per image
+  int n_levels, N, width, P;
+  float* slab;                       // (N, P, width)
+};
+
+// One CTA = 32 consecutive cells (hw) of one level of one image, ALL channels: the input side is ch rows of 32 floats
+// (one 128-byte request per warp and channel), the output side one contiguous block of 32 * ch floats.
+template <bool kUnpack>
+__global__ void __launch_bounds__(256) pack_head_kernel(const PackParams p) {
+  extern __shared__ float tile[];                                   // [ch][33]
+  const int n = blockIdx.y;
+  int t = blockIdx.x, l = 0;
+#pragma unroll
+  for (int q = 1; q < kPackMaxLevels; ++q) l += (q < p.n_levels && t >= p.tile_start[q]) ? 1 : 0;
+  t -= p.tile_start[l];
+  const int ch = p.ch[l], hw = p.hw[l];
+  const int hw0 = t * kTile, nh = min(kTile, hw - hw0);
+  float* lev = p.level[l] + static_cast<size_t>(n) * ch * hw + hw0;                                  // [ch][hw], at cell hw0
+  float* out = p.slab + (static_cast<size_t>(n) * p.P + p.row_off[l]) * p.width + static_cast<size_t>(hw0) * ch;   // [nh][ch]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (!kUnpack) {
+    for (int c = warp; c < ch; c += 8)
+      if (lane < nh) tile[c * (kTile + 1) + lane] = lev[static_cast<size_t>(c) * hw + lane];
+    __syncthreads();
+    for (int h = warp; h < nh; h += 8)
+      for (int c = lane; c < ch; c += 32) out[static_cast<size_t>(h) * ch + c] = tile[c * (kTile + 1) + h];
+  } else {
+    for (int h = warp; h < nh; h += 8)
+      for (int c = lane; c < ch; c += 32) tile[c * (kTile + 1) + h] = out[static_cast<size_t>(h) * ch + c];
+    __syncthreads();
+    for (int c = warp; c < ch; c += 8)
+      if (lane < nh) lev[static_cast<size_t>(c) * hw + lane] = tile[c * (kTile + 1) + lane];
+  }
+}
+
+static int run_pack(float* const* levels, const int* ch, const int* hw, int n_levels, int N, int width, float* slab, int P,
+                    bool unpack, ssdh_stream_t stream, const char* fn) {
+  if (!levels || !ch || !hw || !slab || n_levels <= 0 || N <= 0 || width <= 0 || P <= 0) { set_error("%s: NULL pointer or non-positive dimension", fn); return SSDH_E_ARG; }
+  if (n_levels > kPackMaxLevels) { set_error("%s: at most %d levels (got %d)", fn, kPackMaxLevels, n_levels); return SSDH_E_LIMIT; }
+  if (N > 65535) { set_error("%s: N <= 65535", fn); return SSDH_E_LIMIT; }
+  PackParams p = {};
+  long long rows = 0;
+  int tiles = 0, ch_max = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!levels[l] || ch[l] <= 0 || hw[l] <= 0 || ch[l] % width != 0) {
+      set_error("%s: level %d: NULL pointer, empty shape or channel count %d not a multiple of the row width %d", fn, l, ch[l], width);
+      return SSDH_E_ARG;
+    }
+    p.level[l] = levels[l]; p.ch[l] = ch[l]; p.hw[l] = hw[l];
+    p.row_off[l] = static_cast<int>(rows);
+    rows += static_cast<long long>(hw[l]) * (ch[l] / width);
+    p.tile_start[l] = tiles;
+    tiles += (hw[l] + kTile - 1) / kTile;
+    ch_max = ch[l] > ch_max ? ch[l] : ch_max;
+  }
+  p.tile_start[n_levels] = tiles;
+  if (rows != P) { set_error("%s: the levels hold %lld rows, the slab %d", fn, rows, P); return SSDH_E_ARG; }
+  const size_t smem = static_cast<size_t>(ch_max) * (kTile + 1) * sizeof(float);
+  if (smem > 200 * 1024) { set_error("%s: at most %d channels per level (got %d)", fn, 200 * 1024 / ((kTile + 1) * 4), ch_max); return SSDH_E_LIMIT; }
+  p.n_levels = n_levels; p.N = N; p.width = width; p.P = P; p.slab = slab;
+  const dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(N));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (unpack) {
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(pack_head_kernel<true>), 200 * 1024, fn)) return e;
+    pack_head_kernel<true><<<grid, 256, smem, st>>>(p);
+  } else {
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(pack_head_kernel<false>), 200 * 1024, fn)) return e;
+    pack_head_kernel<false><<<grid, 256, smem, st>>>(p);
+  }
+  return cuda_status(fn);
+}
+
+}  // namespace ssdh
+
+using namespace ssdh;
+
+extern "C" int ssdh_pack_head(const float* const* levels, const int* ch, const int* hw, int n_levels, int N, int width,
+                              float* outputs, int P, ssdh_stream_t stream) {
+  return run_pack(const_cast<float* const*>(reinterpret_cast<const float* const*>(levels)), ch, hw, n_levels, N, width, outputs, P, false, stream, "ssdh_pack_head");
+}
+
+extern "C" int ssdh_unpack_head(const float* grad_outputs, float* const* level_grads, const int* ch, const int* hw, int n_levels, int N,
+                                int width, int P, ssdh_stream_t stream) {
+  return run_pack(level_grads, ch, hw, n_levels, N, width, const_cast<float*>(grad_outputs), P, true, stream, "ssdh_unpack_head");
+}

@@ -97,24 +97,22 @@ class SSD(nn.Module):
         """(N, 3, 300, 300) -> (N, 8732, 4 + C), rows level-major then (cell row, cell col, anchor).
 
         The reference looks detectors up with the activation's name and therefore finds none (ssd.py:102, SURVEY
-        section 0 item 3); the evidently intended ``act_*`` -> ``det_*`` pairing is used here.  Each level is written
-        straight into its slice of the result instead of growing it by concatenation (ssd.py:104)."""
+        section 0 item 3); the evidently intended ``act_*`` -> ``det_*`` pairing is used here.  On the GPU the six detector outputs go through
+        ``ssdh_pack_head``: permute + reshape + cat (ssd.py:103-104) as one pass over the data."""
         n = x.size(0)
         width = self.num_classes + 4
         x = self.normalize(x)
-        parts = []
+        levels = []
         for name, layer in self.features.items():
             x = layer(x)
             det = "det" + name[3:] if name.startswith("act") else None
             if det is not None and det in self.detectors:
-                parts.append(self.detectors[det](x).permute(0, 2, 3, 1).reshape(n, -1, width))
-        total = sum(p.shape[1] for p in parts)
-        y = x.new_empty((n, total, width))
-        at = 0
-        for p in parts:
-            y[:, at:at + p.shape[1]] = p
-            at += p.shape[1]
-        return y
+                levels.append(self.detectors[det](x))
+        if not levels:
+            return x.new_empty((n, 0, width))
+        if levels[0].is_cuda and levels[0].dtype == torch.float32:
+            return ops.pack_head(levels, width)          # one pass: NCHW detector outputs -> (N, 8732, 4 + C) rows
+        return torch.cat([t.permute(0, 2, 3, 1).reshape(n, -1, width) for t in levels], dim=1)    # reference tail (CPU / other dtypes)
 
     def _get_default_bboxes(self) -> torch.Tensor:
         """(8732, 4) priors; kernel ssdh_default_boxes, bit-identical to reference ssd.py:108-133."""

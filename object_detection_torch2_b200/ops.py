@@ -257,6 +257,51 @@ def prefetch_l2(t: torch.Tensor) -> None:
             check(lib.ssdh_prefetch_l2(t.data_ptr(), t.numel() * t.element_size(), _stream()), "ssdh_prefetch_l2")
 
 
+# ------------------------------------------------------------------------------------------------ 8f-1 head producer
+def _pack_call(levels, slab, width, unpack):
+    lib = _lib.load()
+    n_levels = len(levels)
+    N = slab.shape[0]
+    ptrs = (ctypes.c_void_p * n_levels)(*[t.data_ptr() for t in levels])
+    ch = (ctypes.c_int * n_levels)(*[t.shape[1] for t in levels])
+    hw = (ctypes.c_int * n_levels)(*[t.shape[2] * t.shape[3] for t in levels])
+    with torch.cuda.device(slab.device):
+        if unpack:
+            check(lib.ssdh_unpack_head(slab.data_ptr(), ptrs, ch, hw, n_levels, N, width, slab.shape[1], _stream()), "ssdh_unpack_head")
+        else:
+            check(lib.ssdh_pack_head(ptrs, ch, hw, n_levels, N, width, slab.data_ptr(), slab.shape[1], _stream()), "ssdh_pack_head")
+
+
+class _PackHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, width, *levels):
+        levels = [_f32c(t) for t in levels]
+        _need_cuda(*levels)
+        N = levels[0].shape[0]
+        rows = sum(t.shape[1] // width * t.shape[2] * t.shape[3] for t in levels)
+        out = torch.empty((N, rows, width), dtype=torch.float32, device=levels[0].device)
+        _pack_call(levels, out, width, unpack=False)
+        ctx.width = width
+        ctx.shapes = [t.shape for t in levels]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        grad = _f32c(grad)
+        grads = [torch.empty(s, dtype=torch.float32, device=grad.device) for s in ctx.shapes]
+        _pack_call(grads, grad, ctx.width, unpack=True)
+        return (None, *grads)
+
+
+def pack_head(levels, width: int) -> torch.Tensor:
+    """[(N, A_k * width, H_k, W_k)] detector outputs -> (N, sum_k H_k W_k A_k, width): the permute / reshape / cat tail of
+    SSD.forward (reference ssd.py:96-104) as ONE pass; differentiable (the backward is the same kernel run in reverse)."""
+    for t in levels:
+        if t.dim() != 4 or t.shape[1] % width != 0 or t.shape[0] != levels[0].shape[0]:
+            raise ValueError("pack_head: every level must be (N, anchors * width, H, W)")
+    return _PackHeadFn.apply(width, *levels)
+
+
 # ------------------------------------------------------------------------------------------------ I1-I4
 def decode(pr: torch.Tensor, priors: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()

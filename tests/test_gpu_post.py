@@ -223,3 +223,36 @@ def test_compact_detections_and_voc_ap(priors_cpu, priors_gpu):
             want = float("nan") if int(tallies[c, 2]) == 0 else 0.0
         got = float(out["ap_voc"][c])
         assert (np.isnan(want) and np.isnan(got)) or got == pytest.approx(want, rel=1e-5, abs=1e-6), (c, got, want)
+
+
+# ------------------------------------------------------------------------------------------------ 8f-1 head producer
+SSD_LEVELS = [(38, 4), (19, 6), (10, 6), (5, 6), (3, 4), (1, 4)]
+
+
+def _reference_tail(levels, width):
+    n = levels[0].shape[0]
+    return torch.cat([t.permute(0, 2, 3, 1).reshape(n, -1, width) for t in levels], dim=1)      # ssd.py:103-104
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,width,levels", [(3, 25, SSD_LEVELS), (2, 9, [(7, 3), (2, 1), (33, 2)]), (1, 68, [(5, 6)])])
+def test_pack_head_matches_permute_reshape_cat(n, width, levels):
+    """ssdh_pack_head is a bit-exact copy of the reference's forward tail, and its backward routes gradients the same way."""
+    g = torch.Generator().manual_seed(n * 100 + width)
+    xs = [torch.randn(n, a * width, m, m, generator=g).to(DEV).requires_grad_(True) for m, a in levels]
+    out = ops.pack_head(xs, width)
+    want = _reference_tail([x.detach() for x in xs], width)
+    assert out.shape == want.shape and torch.equal(out, want)
+    w = torch.randn(out.shape, generator=g).to(DEV)
+    (out * w).sum().backward()
+    ys = [x.detach().clone().requires_grad_(True) for x in xs]
+    (_reference_tail(ys, width) * w).sum().backward()
+    for x, y in zip(xs, ys):
+        assert torch.equal(x.grad, y.grad)
+
+
+@pytest.mark.gpu
+def test_pack_head_rejects_bad_shapes():
+    x = torch.zeros(2, 26, 3, 3, device=DEV)
+    with pytest.raises(ValueError):
+        ops.pack_head([x], 25)
