@@ -301,6 +301,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_extras:
         line["post"] = bench_post(ops, synth, priors, dev, peak)
+        line["pack_head"] = bench_pack(ops, dev, peak)
         rate, ms, threads, sample = cpu_reference_rate(3, 1, budget_s=15.0)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample}
     if rank == 0:
@@ -351,6 +352,31 @@ def bench_post(ops, synth, priors, dev, peak):
         res[dist_name] = {"batch": n, "ms": ms, "images_per_s": n / (ms * 1e-3), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
                           "candidates_per_image": float(out.order_cnt.float().mean()), "kept_per_image": float(out.keep_cnt.float().mean()),
                           "launches_per_call": 3}
+    return res
+
+
+def bench_pack(ops, dev, peak):
+    """the six detector outputs -> (N, 8732, 25) in one pass (ssdh_pack_head) against the reference's
+    permute / reshape / cat tail (ssd.py:103-104), batch 256, rotating inputs larger than L2."""
+    n = POST_BATCH
+    levels = [(38, 4), (19, 6), (10, 6), (5, 6), (3, 4), (1, 4)]
+    sets = [[torch.randn(n, a * ROW, m, m, device=dev) for m, a in levels] for _ in range(2)]
+    res = {"batch": n}
+    for name, fn in (("ms", lambda xs: ops.pack_head(xs, ROW)),
+                     ("torch_ms", lambda xs: torch.cat([t.permute(0, 2, 3, 1).reshape(n, -1, ROW) for t in xs], dim=1))):
+        for xs in sets:
+            fn(xs)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            for xs in sets:
+                fn(xs)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / (reps * len(sets))
+    res["hbm_frac"] = n * 2 * SLAB / (res["ms"] * 1e-3) / 1e9 / peak
     return res
 
 
