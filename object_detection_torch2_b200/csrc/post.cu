@@ -202,6 +202,20 @@ struct NmsParams {
   unsigned long long* trace;  // debug: [N][16] SM clock stamps, NULL in production
 };
 
+constexpr int kTileC = 256;                        // candidates settled per round of the greedy suppression
+constexpr int kSplit = kNmsThreads / kTileC;       // threads sharing one candidate in the sweep over the kept list
+constexpr int kTileWords = kTileC / 32;
+
+struct NmsTile {                                   // the round's surviving candidates, in score order
+  float4 box[kTileC];                              // x1, x2, y1, y2
+  float area[kTileC];
+  int row[kTileC];
+  uint32_t mask[kTileC][kTileWords];               // mask[r] bit c (c > r): r suppresses c
+  uint8_t cls[kTileC];
+  uint8_t alive[kTileC];
+  uint32_t alive_w[kTileWords], keep_w[kTileWords];
+};
+
 struct NmsShared {
   int warp_total[kNmsWarps];
   int warp_alive[kNmsWarps];
@@ -236,6 +250,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
   float4* k_box = reinterpret_cast<float4*>(region);          // x1, x2, y1, y2
   float* k_area = reinterpret_cast<float*>(k_box + Pp);
   uint8_t* k_cls = reinterpret_cast<uint8_t*>(k_area + Pp);
+  const size_t sort_bytes = Pp * (4 + 4 + 2 + 2) + kNmsWarps * 256 * 2, kept_bytes = Pp * (16 + 4 + 1);
+  NmsTile& tile = *reinterpret_cast<NmsTile*>(region + (((sort_bytes > kept_bytes ? sort_bytes : kept_bytes) + 15) & ~static_cast<size_t>(15)));
 
   const float* key_in = p.cand_key + static_cast<size_t>(n) * P;
   const uint8_t* cls_in = p.cand_cls + static_cast<size_t>(n) * P;
@@ -382,9 +398,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
     }
     return hit;
   };
-  for (int base = 0; base < K; base += kNmsThreads) {
+  // Rounds of kTileC candidates in score order.  (1) every candidate is checked against everything kept so far
+  // (kSplit threads share the sweep over the kept list, broadcast reads); (2) the survivors are compacted and their
+  // mutual overlaps go into a bit matrix, warp per row, one ballot per 32 columns; (3) one warp walks the rows in score
+  // order, OR-ing the masks of the rows it keeps into a register-resident `removed` set -- the sequential greedy rule
+  // (src/utils.py:102-108) at a few instructions per candidate; (4) the kept rows join the kept list.
+  for (int base = 0; base < K; base += kTileC) {
     if (sh.stop) break;
-    const int i = base + tid;
+    const int c = tid / kSplit, part = tid % kSplit;
+    const int i = base + c;
     bool alive = i < K;
     int my_row = 0, my_cls = 0;
     Corners me = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -396,67 +418,87 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
     }
     const float4 me4 = make_float4(me.x1, me.x2, me.y1, me.y2);
     const int kept_before = sh.kept;
-    // (1) against everything kept by earlier tiles: broadcast reads of the kept list
-    for (int j0 = 0; j0 < kept_before; j0 += 32) {
+    for (int j0 = 0; j0 < kept_before; j0 += 32 * kSplit) {
       if (!__any_sync(0xffffffffu, alive)) break;
-      const int j1 = min(j0 + 32, kept_before);
-      for (int j = j0; j < j1; ++j) {
+      const int j1 = min(j0 + 32 * kSplit, kept_before);
+      for (int j = j0 + part; j < j1; j += kSplit) {
         bool hit = suppresses(k_box[j], k_area[j], me4, me.area);
         if (p.per_class) hit = hit && (k_cls[j] == my_cls);
         alive = alive && !hit;
       }
     }
-    {
-      const uint32_t ballot = __ballot_sync(0xffffffffu, alive);
-      if (lane == 0) sh.warp_alive[warp] = static_cast<int>(ballot);
+#pragma unroll
+    for (int o = 1; o < kSplit; o <<= 1) alive = (__shfl_xor_sync(0xffffffffu, alive ? 1 : 0, o) != 0) && alive;
+    if (part == 0) tile.alive[c] = alive ? 1 : 0;
+    __syncthreads();
+    if (warp < kTileWords) {
+      const uint32_t w = __ballot_sync(0xffffffffu, tile.alive[32 * warp + lane] != 0);
+      if (lane == 0) tile.alive_w[warp] = w;
     }
     __syncthreads();
-    // (2) resolve the tile warp by warp, in score order
-    for (int w = 0; w < kNmsWarps; ++w) {
-      if (sh.warp_alive[w] == 0) continue;            // block-uniform
-      if (sh.stop) break;                             // block-uniform (set before a barrier)
-      if (warp == w) {
-        const int kept_now = sh.kept;
-        for (int j = kept_before; j < kept_now; ++j) {            // boxes kept by earlier warps of this tile
-          bool hit = suppresses(k_box[j], k_area[j], me4, me.area);
-          if (p.per_class) hit = hit && (k_cls[j] == my_cls);
-          alive = alive && !hit;
+    int M = 0, my_idx = 0;
+#pragma unroll
+    for (int w = 0; w < kTileWords; ++w) {
+      const uint32_t aw = tile.alive_w[w];
+      if (w < (c >> 5)) my_idx += __popc(aw);
+      else if (w == (c >> 5)) my_idx += __popc(aw & ((1u << (c & 31)) - 1u));
+      M += __popc(aw);
+    }
+    if (alive && part == 0) {
+      tile.box[my_idx] = me4;
+      tile.area[my_idx] = me.area;
+      tile.cls[my_idx] = static_cast<uint8_t>(my_cls);
+      tile.row[my_idx] = my_row;
+    }
+    __syncthreads();
+    const int Mw = (M + 31) >> 5;
+    for (int r = warp; r < M; r += kNmsWarps) {
+      const float4 bi = tile.box[r];
+      const float ai = tile.area[r];
+      const int ci = tile.cls[r];
+      for (int w = r >> 5; w < Mw; ++w) {
+        const int j = 32 * w + lane;
+        bool hit = false;
+        if (j > r && j < M) {
+          hit = suppresses(bi, ai, tile.box[j], tile.area[j]);
+          if (p.per_class) hit = hit && (tile.cls[j] == ci);
         }
-        uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
-        uint32_t todo = alive_mask;
-        while (todo) {
-          const int j = __ffs(todo) - 1;
-          todo &= todo - 1;
-          Corners o;
-          o.x1 = __shfl_sync(0xffffffffu, me.x1, j);
-          o.x2 = __shfl_sync(0xffffffffu, me.x2, j);
-          o.y1 = __shfl_sync(0xffffffffu, me.y1, j);
-          o.y2 = __shfl_sync(0xffffffffu, me.y2, j);
-          o.area = __shfl_sync(0xffffffffu, me.area, j);
-          const int ocls = __shfl_sync(0xffffffffu, my_cls, j);
-          if (alive && lane > j) {
-            bool hit = suppresses(make_float4(o.x1, o.x2, o.y1, o.y2), o.area, me4, me.area);
-            if (p.per_class) hit = hit && (ocls == my_cls);
-            alive = !hit;
-          }
-          alive_mask = __ballot_sync(0xffffffffu, alive);
-          todo &= alive_mask;
-        }
-        const int pos = kept_now + __popc(alive_mask & lt_mask);
-        if (alive && pos < limit) {
-          k_box[pos] = make_float4(me.x1, me.x2, me.y1, me.y2);
-          k_area[pos] = me.area;
-          k_cls[pos] = static_cast<uint8_t>(my_cls);
-          keep[pos] = my_row;
-          atomicOr(&keep_bits[my_row >> 5], 1u << (my_row & 31));
-        }
-        if (lane == 0) {
-          const int total = min(kept_now + __popc(alive_mask), limit);
-          sh.kept = total;
-          if (total >= limit) sh.stop = 1;
-        }
+        const uint32_t word = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) tile.mask[r][w] = word;
       }
-      __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t removed = 0u, keepw = 0u;           // lane w < kTileWords holds word w
+      int total = kept_before;
+      for (int r = 0; r < M; ++r) {
+        const int wr = r >> 5;
+        const uint32_t rem = __shfl_sync(0xffffffffu, removed, wr);
+        if ((rem >> (r & 31)) & 1u) continue;      // uniform
+        if (total >= limit) break;                 // uniform
+        ++total;
+        if (lane == wr) keepw |= 1u << (r & 31);
+        if (lane >= wr && lane < Mw) removed |= tile.mask[r][lane];
+      }
+      if (lane < kTileWords) tile.keep_w[lane] = keepw;
+      if (lane == 0) {
+        sh.kept = total;
+        if (total >= limit) sh.stop = 1;
+      }
+    }
+    __syncthreads();
+    if (tid < M) {
+      const uint32_t kw = tile.keep_w[tid >> 5];
+      if ((kw >> (tid & 31)) & 1u) {
+        int pos = kept_before + __popc(kw & ((1u << (tid & 31)) - 1u));
+        for (int w = 0; w < (tid >> 5); ++w) pos += __popc(tile.keep_w[w]);
+        const int r = tile.row[tid];
+        k_box[pos] = tile.box[tid];
+        k_area[pos] = tile.area[tid];
+        k_cls[pos] = tile.cls[tid];
+        keep[pos] = r;
+        atomicOr(&keep_bits[r >> 5], 1u << (r & 31));
+      }
     }
     __syncthreads();
   }
@@ -839,7 +881,7 @@ static size_t nms_smem_bytes(int P) {
   const size_t head = ((sizeof(NmsShared) + 15) & ~static_cast<size_t>(15)) + ((static_cast<size_t>((P + 31) / 32) * 4 + 15) & ~static_cast<size_t>(15));
   const size_t sort_bytes = Pp * (4 + 4 + 2 + 2) + kNmsWarps * 256 * 2;
   const size_t kept_bytes = Pp * (16 + 4 + 1);
-  return head + (sort_bytes > kept_bytes ? sort_bytes : kept_bytes) + 16;
+  return head + (((sort_bytes > kept_bytes ? sort_bytes : kept_bytes) + 15) & ~static_cast<size_t>(15)) + sizeof(NmsTile) + 16;
 }
 
 struct NmsWorkspace {
