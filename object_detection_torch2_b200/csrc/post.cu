@@ -221,9 +221,10 @@ struct NmsShared {
   int warp_alive[kNmsWarps];
   int part[4][256];
   int digit_base[256];
-  int n_cand, kept, uniform_digit, stop;
+  int n_cand, kept, uniform_digit, stop, odd_kept;
 };
 
+template <bool kPerClass>
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, const int32_t* __restrict__ large) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = blockIdx.x, P = p.P, row = 4 + p.C;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
   int32_t* keep = p.keep + static_cast<size_t>(n) * P;
   float* img = p.outputs + static_cast<size_t>(n) * P * row;
 
-  if (tid == 0) { sh.n_cand = 0; sh.kept = 0; sh.stop = 0; }
+  if (tid == 0) { sh.n_cand = 0; sh.kept = 0; sh.stop = 0; sh.odd_kept = 0; }
   for (int i = tid; i < bit_words; i += kNmsThreads) keep_bits[i] = 0u;
   __syncthreads();
 
@@ -414,18 +415,43 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       my_row = order[i];
       const float* b = img + static_cast<size_t>(my_row) * row;
       me = make_corners(b[0], b[1], b[2], b[3]);
-      if (p.per_class) my_cls = cls_in[my_row];
+      if (kPerClass) my_cls = cls_in[my_row];
     }
     const float4 me4 = make_float4(me.x1, me.x2, me.y1, me.y2);
     const int kept_before = sh.kept;
-    for (int j0 = 0; j0 < kept_before; j0 += 32 * kSplit) {
-      if (!__any_sync(0xffffffffu, alive)) break;
-      const int j1 = min(j0 + 32 * kSplit, kept_before);
-      for (int j = j0 + part; j < j1; j += kSplit) {
-        bool hit = suppresses(k_box[j], k_area[j], me4, me.area);
-        if (p.per_class) hit = hit && (k_cls[j] == my_cls);
-        alive = alive && !hit;
+    {
+      // fast sweep: no per-pair branch; the band test needs positive finite areas on both sides (odd boxes are flagged
+      // when they enter the kept list) and flags a borderline pair through `slack`; both cases redo the sweep exactly
+      const bool tame = pt.usable && sh.odd_kept == 0 && me.area >= 1e-30f && me.area <= 1e30f;
+      float slack = 1.0f;
+      bool dead = false;
+      for (int j0 = 0; j0 < kept_before; j0 += 32 * kSplit) {
+        if (!__any_sync(0xffffffffu, alive && !dead)) break;
+        const int j1 = min(j0 + 32 * kSplit, kept_before);
+        for (int j = j0 + part; j < j1; j += kSplit) {
+          const float4 kb = k_box[j];
+          const float wd = fmaxf(fminf(kb.y, me4.y) - fmaxf(kb.x, me4.x), 0.0f);
+          const float ht = fmaxf(fminf(kb.w, me4.w) - fmaxf(kb.z, me4.z), 0.0f);
+          const float inter = wd * ht;
+          const float uni = (k_area[j] + me.area) - inter;
+          const float e = fmaf(uni, pt.nthr, inter), m = uni * pt.eps;
+          slack = fminf(slack, fabsf(e) - m);
+          bool hit = e > m;
+          if (kPerClass) hit = hit && (k_cls[j] == my_cls);
+          dead |= hit;
+        }
       }
+      if (__any_sync(0xffffffffu, alive && (!tame || !(slack > 0.0f)))) {     // rare: settle this candidate with the IEEE division
+        if (alive && (!tame || !(slack > 0.0f))) {
+          dead = false;
+          for (int j = part; j < kept_before && !dead; j += kSplit) {
+            bool hit = suppresses(k_box[j], k_area[j], me4, me.area);
+            if (kPerClass) hit = hit && (k_cls[j] == my_cls);
+            dead = hit;
+          }
+        }
+      }
+      alive = alive && !dead;
     }
 #pragma unroll
     for (int o = 1; o < kSplit; o <<= 1) alive = (__shfl_xor_sync(0xffffffffu, alive ? 1 : 0, o) != 0) && alive;
@@ -461,7 +487,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
         bool hit = false;
         if (j > r && j < M) {
           hit = suppresses(bi, ai, tile.box[j], tile.area[j]);
-          if (p.per_class) hit = hit && (tile.cls[j] == ci);
+          if (kPerClass) hit = hit && (tile.cls[j] == ci);
         }
         const uint32_t word = __ballot_sync(0xffffffffu, hit);
         if (lane == 0) tile.mask[r][w] = word;
@@ -495,6 +521,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
         const int r = tile.row[tid];
         k_box[pos] = tile.box[tid];
         k_area[pos] = tile.area[tid];
+        if (!(tile.area[tid] >= 1e-30f && tile.area[tid] <= 1e30f)) sh.odd_kept = 1;
         k_cls[pos] = tile.cls[tid];
         keep[pos] = r;
         atomicOr(&keep_bits[r >> 5], 1u << (r & 31));
@@ -921,7 +948,8 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   nms_ws_layout(N, P, ws, &w);
   const int row = 4 + C;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_score_kernel), 96 * 1024, fn)) return e;
-  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel), 227 * 1024, fn)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel<false>), 227 * 1024, fn)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel<true>), 227 * 1024, fn)) return e;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel<false>), 100 * 1024, fn)) return e;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel<true>), 100 * 1024, fn)) return e;
   NmsParams p;
@@ -986,7 +1014,8 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
                             : launch(nms_small_kernel<false>, static_cast<unsigned>(nk), kSmallThreads, small_smem, true, pk, w.large + n0)) return e;
     }
   }
-  return launch(nms_kernel, static_cast<unsigned>(N), kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
+  if (per_class) return launch(nms_kernel<true>, static_cast<unsigned>(N), kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
+  return launch(nms_kernel<false>, static_cast<unsigned>(N), kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
 }
 
 }  // namespace ssdh
