@@ -224,6 +224,10 @@ struct NmsShared {
   int n_cand, kept, uniform_digit, stop, odd_kept;
 };
 
+// Debug stamps (ssdh_debug_set_nms_trace): [image][16] SM clocks.
+#define NMS_TRACE(idx) do { if (p.trace != nullptr && threadIdx.x == 0) p.trace[static_cast<size_t>(blockIdx.x) * 16 + (idx)] = clock64(); } while (0)
+#define NMS_ACC(var, t0) do { if (p.trace != nullptr && threadIdx.x == 0) { const long long now_ = clock64(); var += now_ - (t0); t0 = now_; } } while (0)
+
 template <bool kPerClass>
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, const int32_t* __restrict__ large) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
   float* img = p.outputs + static_cast<size_t>(n) * P * row;
 
   if (tid == 0) { sh.n_cand = 0; sh.kept = 0; sh.stop = 0; sh.odd_kept = 0; }
+  NMS_TRACE(0);
   for (int i = tid; i < bit_words; i += kNmsThreads) keep_bits[i] = 0u;
   __syncthreads();
 
@@ -289,6 +294,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
     __syncthreads();
   }
   const int K = sh.n_cand;
+  NMS_TRACE(1);
 
   // ---- B. stable LSD radix sort of (key, idx) -------------------------------------------------------------
   {
@@ -383,6 +389,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
     __syncthreads();
   }
 
+  NMS_TRACE(2);
+  long long t_sweep = 0, t_matrix = 0, t_walk = 0, t_mark = p.trace != nullptr ? clock64() : 0;
   // ---- C. greedy suppression -----------------------------------------------------------------------------
   const ThrBand band = p.band;
   const PairThr pt = make_pair_thr(band.thr);
@@ -477,6 +485,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       tile.row[my_idx] = my_row;
     }
     __syncthreads();
+    NMS_ACC(t_sweep, t_mark);
     const int Mw = (M + 31) >> 5;
     for (int r = warp; r < M; r += kNmsWarps) {
       const float4 bi = tile.box[r];
@@ -494,6 +503,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       }
     }
     __syncthreads();
+    NMS_ACC(t_matrix, t_mark);
     if (warp == 0) {
       uint32_t removed = 0u, keepw = 0u;           // lane w < kTileWords holds word w
       int total = kept_before;
@@ -528,9 +538,16 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       }
     }
     __syncthreads();
+    NMS_ACC(t_walk, t_mark);
   }
   __syncthreads();
   const int kept = sh.kept;
+  NMS_TRACE(3);
+  if (p.trace != nullptr && tid == 0) {
+    p.trace[static_cast<size_t>(blockIdx.x) * 16 + 9] = t_sweep;
+    p.trace[static_cast<size_t>(blockIdx.x) * 16 + 10] = t_matrix;
+    p.trace[static_cast<size_t>(blockIdx.x) * 16 + 11] = t_walk;
+  }
   if (tid == 0) {
     if (p.keep_cnt) p.keep_cnt[n] = kept;
     if (p.order_cnt) p.order_cnt[n] = K;
@@ -583,7 +600,6 @@ struct SmallShared {
   int n_cand, uniform_digit, kept;
 };
 
-#define NMS_TRACE(idx) do { if (p.trace != nullptr && threadIdx.x == 0) p.trace[static_cast<size_t>(blockIdx.x) * 16 + (idx)] = clock64(); } while (0)
 static unsigned long long* g_nms_trace = nullptr;
 
 template <bool kPerClass>
