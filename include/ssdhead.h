@@ -130,6 +130,12 @@ SSDH_API int ssdh_pack_head(const float* const* levels, const int* ch, const int
 SSDH_API int ssdh_unpack_head(const float* grad_outputs, float* const* level_grads, const int* ch, const int* hw, int n_levels,
                               int N, int width, int P, ssdh_stream_t stream);
 
+/* SURVEY 8f-3 -- ground-truth ingest, the device side of collate_fn (src/utils.py:8-16): compact rows
+ * [cx, cy, w, h, label] (N, G, 5) fp32 and the per-image row counts lengths[N] (NULL: every row is real) are expanded
+ * into the dense zero-padded one-hot tensor targets (N, G, 4 + C) that pad_sequence would have produced.  label is a
+ * class index 0..C-1 stored as a float (0 = void). */
+SSDH_API int ssdh_expand_targets(const float* compact, const int* lengths, int N, int G, int C, float* targets, ssdh_stream_t stream);
+
 /* grad *= *scale (device scalar), skipped entirely when *scale == 1: the autograd chain-rule hook. */
 SSDH_API int ssdh_scale_inplace(float* x, size_t n, const float* scale, ssdh_stream_t stream);
 

@@ -39,6 +39,7 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "ssdh_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "ssdh_prefetch_l2": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "ssdh_expand_targets": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ssdh_pack_head": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ssdh_unpack_head": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ssdh_decode": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p]),

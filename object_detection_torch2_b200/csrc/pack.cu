@@ -104,3 +104,43 @@ extern "C" int ssdh_unpack_head(const float* grad_outputs, float* const* level_g
                                 int width, int P, ssdh_stream_t stream) {
   return run_pack(level_grads, ch, hw, n_levels, N, width, const_cast<float*>(grad_outputs), P, true, stream, "ssdh_unpack_head");
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// ground-truth ingest.  The reference ships dense one-hot rows [cx, cy, w, h, onehot(C)] zero-padded to the
+// batch maximum by pad_sequence (src/utils.py:8-16): 100 bytes per row over PCIe for 5 numbers of information.  The host
+// sends compact rows [cx, cy, w, h, label] (+ the per-image row counts) and this kernel expands them on the device into
+// exactly the tensor collate_fn would have produced, which every other entry point takes unchanged.
+namespace ssdh {
+
+__global__ void __launch_bounds__(256) expand_targets_kernel(const float* __restrict__ compact, const int* __restrict__ lengths,
+                                                             int N, int G, int C, float* __restrict__ dense) {
+  const int width = 4 + C;
+  const long long total = static_cast<long long>(N) * G * width;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % width);
+    const long long rg = i / width;                       // row index n * G + g
+    const int g = static_cast<int>(rg % G), n = static_cast<int>(rg / G);
+    const bool real = lengths == nullptr || g < lengths[n];
+    const float* src = compact + rg * 5;
+    float v = 0.0f;
+    if (real) {
+      if (c < 4) v = src[c];
+      else v = (static_cast<int>(src[4]) == c - 4) ? 1.0f : 0.0f;
+    }
+    dense[i] = v;
+  }
+}
+
+}  // namespace ssdh
+
+extern "C" int ssdh_expand_targets(const float* compact, const int* lengths, int N, int G, int C, float* targets, ssdh_stream_t stream) {
+  if (N < 0 || G < 0 || C <= 0 || (static_cast<long long>(N) * G > 0 && (!compact || !targets))) {
+    set_error("ssdh_expand_targets: NULL pointer or bad dimension");
+    return SSDH_E_ARG;
+  }
+  const long long total = static_cast<long long>(N) * G * (4 + C);
+  if (total == 0) return 0;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);      // 148 SMs x 8
+  ssdh::expand_targets_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(compact, lengths, N, G, C, targets);
+  return ssdh::cuda_status("ssdh_expand_targets");
+}

@@ -302,6 +302,27 @@ def pack_head(levels, width: int) -> torch.Tensor:
     return _PackHeadFn.apply(width, *levels)
 
 
+# ------------------------------------------------------------------------------------------------ 8f-3 ground-truth ingest
+def expand_targets(compact: torch.Tensor, lengths: Optional[torch.Tensor], num_classes: int) -> torch.Tensor:
+    """(N, G, 5) rows [cx, cy, w, h, label] (+ per-image row counts) -> the dense zero-padded one-hot (N, G, 4 + C) tensor
+    the reference's collate_fn builds on the host (src/utils.py:8-16)."""
+    lib = _lib.load()
+    _need_cuda(compact)
+    compact = _f32c(compact)
+    N, G, five = compact.shape
+    if five != 5:
+        raise ValueError("expand_targets: compact rows are [cx, cy, w, h, label]")
+    if lengths is not None:
+        _need_cuda(lengths)
+        lengths = lengths.to(torch.int32).contiguous()
+        if lengths.numel() != N:
+            raise ValueError("expand_targets: one length per image")
+    out = torch.empty((N, G, 4 + num_classes), dtype=torch.float32, device=compact.device)
+    with torch.cuda.device(compact.device):
+        check(lib.ssdh_expand_targets(compact.data_ptr(), _ptr(lengths), N, G, num_classes, out.data_ptr(), _stream()), "ssdh_expand_targets")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ I1-I4
 def decode(pr: torch.Tensor, priors: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()

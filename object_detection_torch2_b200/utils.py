@@ -58,3 +58,31 @@ def detect(outputs: torch.Tensor, df: torch.Tensor, iou_thresh: float = 0.5, sco
     Replaces the dense tensor walk of reference src/inference.py:71-81."""
     res = ops.postprocess_(outputs, df, iou_thresh, score_thresh, top_k, per_class, want_lists=True)
     return ops.gather_detections(outputs, res.keep, res.keep_cnt, max_det=int(top_k or outputs.shape[1]))
+
+
+def collate_fn_compact(batch, pin_memory: bool = True):
+    """Drop-in for the reference's ``collate_fn`` (src/utils.py:8-16) that ships the ground truth compactly.
+
+    ``batch`` is the dataset's list of ``(image, gt)`` with ``gt`` of shape (G_i, 4 + C) one-hot rows.  Returns
+    ``(images, compact, lengths)``: ``compact`` (N, G, 5) rows ``[cx, cy, w, h, label]`` zero-padded to the batch
+    maximum and ``lengths`` (N,) int32, both in pinned host memory so the H2D copies can be asynchronous.  On the device
+    ``targets_from_compact`` rebuilds exactly the tensor ``pad_sequence`` would have produced (100 -> 20 bytes per row)."""
+    images = torch.stack([img for img, _ in batch], dim=0)
+    gmax = max((int(gt.shape[0]) for _, gt in batch), default=0)
+    compact = torch.zeros((len(batch), gmax, 5), dtype=torch.float32)
+    lengths = torch.zeros((len(batch),), dtype=torch.int32)
+    for n, (_, gt) in enumerate(batch):
+        g = int(gt.shape[0])
+        lengths[n] = g
+        if g:
+            compact[n, :g, :4] = gt[:, :4]
+            compact[n, :g, 4] = gt[:, 4:].argmax(dim=1).to(torch.float32)
+    if pin_memory and torch.cuda.is_available():
+        compact, lengths = compact.pin_memory(), lengths.pin_memory()
+    return images, compact, lengths
+
+
+def targets_from_compact(compact: torch.Tensor, lengths: torch.Tensor, num_classes: int, device=None) -> torch.Tensor:
+    """Asynchronous H2D of the compact ground truth + on-device expansion to the dense (N, G, 4 + C) targets of SSD.loss."""
+    device = device if device is not None else (compact.device if compact.is_cuda else "cuda")
+    return ops.expand_targets(compact.to(device, non_blocking=True), lengths.to(device, non_blocking=True), num_classes)

@@ -256,3 +256,26 @@ def test_pack_head_rejects_bad_shapes():
     x = torch.zeros(2, 26, 3, 3, device=DEV)
     with pytest.raises(ValueError):
         ops.pack_head([x], 25)
+
+
+# ------------------------------------------------------------------------------------------------ 8f-3 ground-truth ingest
+@pytest.mark.gpu
+def test_compact_ground_truth_round_trip_equals_pad_sequence():
+    """collate_fn_compact + ssdh_expand_targets rebuild exactly what the reference's collate_fn (pad_sequence) builds."""
+    from torch.nn.utils.rnn import pad_sequence
+    g = torch.Generator().manual_seed(3)
+    batch = []
+    for n, rows in enumerate([3, 0, 7, 1]):
+        gt = torch.zeros(rows, 25)
+        gt[:, :4] = torch.rand(rows, 4, generator=g)
+        labels = torch.randint(1, 21, (rows,), generator=g)
+        gt[torch.arange(rows), 4 + labels] = 1.0
+        batch.append((torch.zeros(3, 4, 4), gt))
+    want = pad_sequence([gt for _, gt in batch], batch_first=True)                 # src/utils.py:15
+    images, compact, lengths = utils.collate_fn_compact(batch)
+    assert images.shape == (4, 3, 4, 4) and compact.shape == (4, 7, 5) and lengths.tolist() == [3, 0, 7, 1]
+    got = utils.targets_from_compact(compact, lengths, 21)
+    assert torch.equal(got.cpu(), want)
+    # without lengths every row is taken as real: zero rows then carry the void label like any other row would
+    full = ops.expand_targets(compact.to(DEV), None, 21).cpu()
+    assert torch.equal(full[2], want[2]) and float(full[1, 0, 4]) == 1.0
