@@ -28,6 +28,17 @@ def test_library_exports_header_symbols():
     assert lib.ssdh_default_boxes(None, None) == -1
     assert b"NULL" in lib.ssdh_last_error()
     assert lib.ssdh_multibox_loss(None, None, None, 1, 1, 1, 1, 1.0, 0.25, 1, None, None, None, None, 0, None) == -1
+    # the "next row" entry points validate their arguments before touching the device as well
+    import ctypes
+    assert lib.ssdh_pack_head(None, None, None, 1, 1, 25, None, 1, None) == -1
+    ptrs, ch, hw = (ctypes.c_void_p * 1)(1), (ctypes.c_int * 1)(26), (ctypes.c_int * 1)(4)
+    assert lib.ssdh_pack_head(ptrs, ch, hw, 1, 1, 25, 1, 4, None) == -1 and b"multiple of the row width" in lib.ssdh_last_error()
+    ch[0] = 50
+    assert lib.ssdh_pack_head(ptrs, ch, hw, 1, 1, 25, 1, 9, None) == -1 and b"rows" in lib.ssdh_last_error()
+    assert lib.ssdh_pack_head(ptrs, ch, hw, 9, 1, 25, 1, 8, None) == -2          # SSDH_E_LIMIT: more than 8 levels
+    assert lib.ssdh_unpack_head(None, None, None, None, 1, 1, 25, 1, None) == -1
+    assert lib.ssdh_expand_targets(None, None, 2, 3, 21, None, None) == -1
+    assert lib.ssdh_expand_targets(None, None, 0, 3, 21, None, None) == 0         # nothing to do
 
 
 def test_stats_struct_layout():
