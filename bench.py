@@ -329,7 +329,10 @@ def bench_post(ops, synth, priors, dev, peak):
     greedy suppression is fp32-compute-bound by construction -- SURVEY 7.3-4).  Each call is replayed from a CUDA
     graph (3 kernels, no host gaps) on a freshly restored input; the restore copy is outside the timed region."""
     res = {}
-    for dist_name, reps in (("D2", 20), ("D1", 3)):
+    # D2 / D1: the reference's own call (class-agnostic, no score cut, no top-k; iou_thresh passed explicitly);
+    # D2_north_star: the wording of configs[2] -- score threshold 0.01, per-class NMS 0.45, top-200 (opt-in kwargs)
+    variants = (("D2", "D2", 20, {}), ("D2_north_star", "D2", 20, {"score_thresh": 0.01, "top_k": 200, "per_class": True}), ("D1", "D1", 3, {}))
+    for key, dist_name, reps, kw in variants:
         n = POST_BATCH if dist_name == "D2" else 32
         src = synth.make_outputs(n, 5, dist_name).to(dev)
         bufs = [src.clone() for _ in range(2 if dist_name == "D2" else 1)]        # 2 x 224 MB > L2
@@ -339,11 +342,11 @@ def bench_post(ops, synth, priors, dev, peak):
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for b in bufs:
-                out = ops.postprocess_(b, priors, iou_thresh=0.45, want_lists=True)      # warm-up + workspace allocation
+                out = ops.postprocess_(b, priors, iou_thresh=0.45, want_lists=True, **kw)      # warm-up + workspace allocation
                 b.copy_(src)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=s):
-                    out = ops.postprocess_(b, priors, iou_thresh=0.45, want_lists=True)
+                    out = ops.postprocess_(b, priors, iou_thresh=0.45, want_lists=True, **kw)
                 graphs.append((g, out))
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
@@ -362,7 +365,7 @@ def bench_post(ops, synth, priors, dev, peak):
                 times.append(e0.elapsed_time(e1))
         ms = statistics.median(times)
         alg = n * 2 * SLAB
-        res[dist_name] = {"batch": n, "ms": ms, "images_per_s": n / (ms * 1e-3), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
+        res[key] = {"batch": n, "ms": ms, "images_per_s": n / (ms * 1e-3), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
                           "candidates_per_image": float(out.order_cnt.float().mean()), "kept_per_image": float(out.keep_cnt.float().mean()),
                           "launches_per_call": 3}
     return res
