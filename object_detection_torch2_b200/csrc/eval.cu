@@ -23,8 +23,7 @@ struct EvalParams {
   int* status;                   // workspace: set to 1 if an image had more than P detections
 };
 
-struct Det {
-  float score;
+struct Det {          // 4 bytes: the score is re-read from the slab when a claim is made (keeps five images per SM)
   uint16_t row;
   uint8_t cls;      // 0-based non-void class
   uint8_t best_g;   // 255 = no valid claim
@@ -76,18 +75,53 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams p) 
     gt_cnt[c] = cnt;
   }
 
-  // detections: every positive entry of the score columns 5.. (coalesced flat scan of the image slab)
+  // detections: every positive entry of the score columns 5.. (coalesced flat scan of the image slab, 16 bytes per
+  // load when the slab allows).  The decoded box columns are positive in every row, so the column of each element is
+  // tracked incrementally (no division) and only score columns are examined; after NMS a few hundred entries per image
+  // are positive and only those pay for the row / column split.
   const int total = P * row;
-  for (int i = tid; i < total; i += kEvalThreads) {
-    const float v = img[i];
-    if (!(v > 0.0f)) continue;
+  auto take = [&](int i, float v) {
+    if (!(v > 0.0f)) return;
     const int r = i / row, c = i - r * row;
-    if (c < 5) continue;
+    if (c < 5) return;
     const int slot = atomicAdd(n_det, 1);
     if (slot < P) {
       Det d;
-      d.score = v; d.row = static_cast<uint16_t>(r); d.cls = static_cast<uint8_t>(c - 5); d.best_g = 255;
+      d.row = static_cast<uint16_t>(r); d.cls = static_cast<uint8_t>(c - 5); d.best_g = 255;
       dets[slot] = d;
+    }
+  };
+  if ((reinterpret_cast<uintptr_t>(img) & 15u) == 0 && (total & 3) == 0 && row >= 8) {
+    const float4* img4 = reinterpret_cast<const float4*>(img);
+    const int total4 = total >> 2;
+    constexpr int kBatch = 8;                                  // loads in flight per thread before any of them is examined
+    const int step = (4 * kEvalThreads) % row;                 // column advance between consecutive loads of a thread
+    int col = (4 * tid) % row;                                 // column of the first element of the next load
+    for (int q0 = tid; q0 < total4; q0 += kBatch * kEvalThreads) {
+      float4 v[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int q = q0 + k * kEvalThreads;
+        v[k] = q < total4 ? __ldg(img4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int c0 = col;
+        col += step;
+        if (col >= row) col -= row;
+        // score columns among the four elements: column c0 + j (mod row) >= 5
+        const int c1 = c0 + 1 >= row ? c0 + 1 - row : c0 + 1, c2 = c0 + 2 >= row ? c0 + 2 - row : c0 + 2, c3 = c0 + 3 >= row ? c0 + 3 - row : c0 + 3;
+        const bool hit = (v[k].x > 0.0f && c0 >= 5) || (v[k].y > 0.0f && c1 >= 5) || (v[k].z > 0.0f && c2 >= 5) || (v[k].w > 0.0f && c3 >= 5);
+        if (hit) {
+          const int q = q0 + k * kEvalThreads;
+          take(4 * q + 0, v[k].x); take(4 * q + 1, v[k].y); take(4 * q + 2, v[k].z); take(4 * q + 3, v[k].w);
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < total; i += kEvalThreads) {
+      const float v = img[i];
+      if (v > 0.0f && i % row >= 5) take(i, v);
     }
   }
   __syncthreads();
@@ -111,7 +145,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams p) 
       if (v > best) { best = v; bg = g; }
     }
     if (bg >= 0 && best > p.band.thr) {                   // evaluate.py:147
-      const unsigned long long key = (static_cast<unsigned long long>(~float_key(d.score)) << 32) | d.row;
+      const unsigned long long key = (static_cast<unsigned long long>(~float_key(b[5 + c])) << 32) | d.row;
       atomicMin(&claim[c * G + bg], key);
       dets[i].best_g = static_cast<uint8_t>(bg);
     }
@@ -122,7 +156,8 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams p) 
     const Det d = dets[i];
     bool tp = false;
     if (d.best_g != 255) {
-      const unsigned long long key = (static_cast<unsigned long long>(~float_key(d.score)) << 32) | d.row;
+      const float score = img[static_cast<size_t>(d.row) * row + 5 + d.cls];
+      const unsigned long long key = (static_cast<unsigned long long>(~float_key(score)) << 32) | d.row;
       tp = claim[d.cls * G + d.best_g] == key;            // first claimant in score order, evaluate.py:148
     }
     if (tp) atomicAdd(&tp_cnt[d.cls], 1);
