@@ -103,7 +103,9 @@ decode_score_kernel(float* __restrict__ outputs, const float4* __restrict__ prio
   if (threadIdx.x < rows) {
     float* r = tile + threadIdx.x * row;
     const size_t grow = r0 + threadIdx.x;
-    const float4 box = decode_row(r[0], r[1], r[2], r[3], priors[grow % P]);
+    int pi = static_cast<int>(r0 % static_cast<size_t>(P)) + static_cast<int>(threadIdx.x);       // grow % P without a 64-bit division per row
+    while (pi >= P) pi -= P;
+    const float4 box = decode_row(r[0], r[1], r[2], r[3], priors[pi]);
     int best;
     const float s = best_score([&](int c) { return r[4 + c]; }, C, best);
     r[0] = box.x; r[1] = box.y; r[2] = box.z; r[3] = box.w;
