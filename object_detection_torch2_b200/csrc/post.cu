@@ -507,16 +507,29 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
     __syncthreads();
     NMS_ACC(t_matrix, t_mark);
     if (warp == 0) {
+      // word by word: the 32 rows of a word are settled on registers (lane l holds the bits of later rows of the SAME word
+      // that row l suppresses, fetched by shuffle), then the kept rows' masks are OR-ed into the later words
       uint32_t removed = 0u, keepw = 0u;           // lane w < kTileWords holds word w
       int total = kept_before;
-      for (int r = 0; r < M; ++r) {
-        const int wr = r >> 5;
-        const uint32_t rem = __shfl_sync(0xffffffffu, removed, wr);
-        if ((rem >> (r & 31)) & 1u) continue;      // uniform
-        if (total >= limit) break;                 // uniform
-        ++total;
-        if (lane == wr) keepw |= 1u << (r & 31);
-        if (lane >= wr && lane < Mw) removed |= tile.mask[r][lane];
+      for (int wr = 0; wr < Mw; ++wr) {
+        uint32_t cur = __shfl_sync(0xffffffffu, removed, wr);
+        const int r_mine = 32 * wr + lane;
+        const uint32_t intra = r_mine < M ? tile.mask[r_mine][wr] : 0u;
+        const int rows_here = min(32, M - 32 * wr);
+        uint32_t keptbits = 0u;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+          const uint32_t ib = __shfl_sync(0xffffffffu, intra, b);
+          const bool take = b < rows_here && !((cur >> b) & 1u) && total < limit;     // uniform
+          if (take) { keptbits |= 1u << b; cur |= ib; ++total; }
+        }
+        if (lane == wr) keepw = keptbits;
+        uint32_t todo = keptbits;
+        while (todo) {                             // uniform
+          const int r = 32 * wr + __ffs(todo) - 1;
+          todo &= todo - 1;
+          if (lane > wr && lane < Mw) removed |= tile.mask[r][lane];
+        }
       }
       if (lane < kTileWords) tile.keep_w[lane] = keepw;
       if (lane == 0) {
