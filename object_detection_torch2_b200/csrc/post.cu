@@ -12,7 +12,11 @@
 //   D. score columns of rows that were not kept are zeroed (src/utils.py:114).
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ssdh {
 
@@ -207,6 +211,7 @@ struct NmsParams {
 constexpr int kTileC = 256;                        // candidates settled per round of the greedy suppression
 constexpr int kSplit = kNmsThreads / kTileC;       // threads sharing one candidate in the sweep over the kept list
 constexpr int kTileWords = kTileC / 32;
+constexpr int kNmsCluster = 4;                    // CTAs (SMs) sharing a dense image: the kept list is dealt round-robin to them
 
 struct NmsTile {                                   // the round's surviving candidates, in score order
   float4 box[kTileC];                              // x1, x2, y1, y2
@@ -216,6 +221,7 @@ struct NmsTile {                                   // the round's surviving cand
   uint8_t cls[kTileC];
   uint8_t alive[kTileC];
   uint32_t alive_w[kTileWords], keep_w[kTileWords];
+  uint32_t alive_x[2][kNmsCluster][kTileWords];    // per round parity: every CTA's verdict on the round's candidates (written remotely)
 };
 
 struct NmsShared {
@@ -227,13 +233,20 @@ struct NmsShared {
 };
 
 // Debug stamps (ssdh_debug_set_nms_trace): [image][16] SM clocks.
-#define NMS_TRACE(idx) do { if (p.trace != nullptr && threadIdx.x == 0) p.trace[static_cast<size_t>(blockIdx.x) * 16 + (idx)] = clock64(); } while (0)
-#define NMS_ACC(var, t0) do { if (p.trace != nullptr && threadIdx.x == 0) { const long long now_ = clock64(); var += now_ - (t0); t0 = now_; } } while (0)
+#define NMS_TRACE(idx) do { if (p.trace != nullptr && threadIdx.x == 0 && trace_on) p.trace[trace_slot * 16 + (idx)] = clock64(); } while (0)
+#define NMS_ACC(var, t0) do { if (p.trace != nullptr && threadIdx.x == 0 && trace_on) { const long long now_ = clock64(); var += now_ - (t0); t0 = now_; } } while (0)
 
-template <bool kPerClass>
+// kCl = 1: one CTA per image.  kCl = kNmsCluster: a cluster of CTAs per image; every CTA runs the same rounds on the same
+// candidates but sweeps only ITS share of the kept list (entry g lives in CTA g % kCl), the verdicts are AND-ed through
+// distributed shared memory once per round, and the (cheap) matrix / walk steps run redundantly so that nothing else has to
+// be exchanged.  CTA 0 owns every global write.
+template <bool kPerClass, int kCl>
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, const int32_t* __restrict__ large) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = blockIdx.x, P = p.P, row = 4 + p.C;
+  const int n = blockIdx.x / kCl, P = p.P, row = 4 + p.C;
+  const int rank = kCl > 1 ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
+  const bool trace_on = rank == 0;
+  const size_t trace_slot = static_cast<size_t>(n);
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (large != nullptr && large[n] == 0) return;          // already handled by nms_small_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -429,15 +442,16 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
     }
     const float4 me4 = make_float4(me.x1, me.x2, me.y1, me.y2);
     const int kept_before = sh.kept;
+    const int kept_local = kept_before > rank ? (kept_before - rank + kCl - 1) / kCl : 0;      // my share of the kept list
     {
       // fast sweep: no per-pair branch; the band test needs positive finite areas on both sides (odd boxes are flagged
       // when they enter the kept list) and flags a borderline pair through `slack`; both cases redo the sweep exactly
       const bool tame = pt.usable && sh.odd_kept == 0 && me.area >= 1e-30f && me.area <= 1e30f;
       float slack = 1.0f;
       bool dead = false;
-      for (int j0 = 0; j0 < kept_before; j0 += 32 * kSplit) {
+      for (int j0 = 0; j0 < kept_local; j0 += 32 * kSplit) {
         if (!__any_sync(0xffffffffu, alive && !dead)) break;
-        const int j1 = min(j0 + 32 * kSplit, kept_before);
+        const int j1 = min(j0 + 32 * kSplit, kept_local);
         for (int j = j0 + part; j < j1; j += kSplit) {
           const float4 kb = k_box[j];
           const float wd = fmaxf(fminf(kb.y, me4.y) - fmaxf(kb.x, me4.x), 0.0f);
@@ -454,7 +468,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       if (__any_sync(0xffffffffu, alive && (!tame || !(slack > 0.0f)))) {     // rare: settle this candidate with the IEEE division
         if (alive && (!tame || !(slack > 0.0f))) {
           dead = false;
-          for (int j = part; j < kept_before && !dead; j += kSplit) {
+          for (int j = part; j < kept_local && !dead; j += kSplit) {
             bool hit = suppresses(k_box[j], k_area[j], me4, me.area);
             if (kPerClass) hit = hit && (k_cls[j] == my_cls);
             dead = hit;
@@ -472,6 +486,24 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       if (lane == 0) tile.alive_w[warp] = w;
     }
     __syncthreads();
+    if (kCl > 1) {
+      // AND of the verdicts of all CTAs: everyone stores its words into everyone's buffer, one cluster barrier
+      cg::cluster_group cluster = cg::this_cluster();
+      const int par = (base / kTileC) & 1;
+      if (tid < kCl * kTileWords) {
+        const int dst = tid / kTileWords, w = tid % kTileWords;
+        cluster.map_shared_rank(&tile.alive_x[par][rank][w], dst)[0] = tile.alive_w[w];
+      }
+      cluster.sync();
+      if (tid < kTileWords) {
+        uint32_t a = 0xffffffffu;
+#pragma unroll
+        for (int q = 0; q < kCl; ++q) a &= tile.alive_x[par][q][tid];
+        tile.alive_w[tid] = a;
+      }
+      __syncthreads();
+      alive = alive && ((tile.alive_w[c >> 5] >> (c & 31)) & 1u) != 0u;
+    }
     int M = 0, my_idx = 0;
 #pragma unroll
     for (int w = 0; w < kTileWords; ++w) {
@@ -544,24 +576,33 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
         int pos = kept_before + __popc(kw & ((1u << (tid & 31)) - 1u));
         for (int w = 0; w < (tid >> 5); ++w) pos += __popc(tile.keep_w[w]);
         const int r = tile.row[tid];
-        k_box[pos] = tile.box[tid];
-        k_area[pos] = tile.area[tid];
-        if (!(tile.area[tid] >= 1e-30f && tile.area[tid] <= 1e30f)) sh.odd_kept = 1;
-        k_cls[pos] = tile.cls[tid];
-        keep[pos] = r;
-        atomicOr(&keep_bits[r >> 5], 1u << (r & 31));
+        if (pos % kCl == rank) {                  // my share of the kept list
+          const int lp = pos / kCl;
+          k_box[lp] = tile.box[tid];
+          k_area[lp] = tile.area[tid];
+          if (!(tile.area[tid] >= 1e-30f && tile.area[tid] <= 1e30f)) sh.odd_kept = 1;
+          k_cls[lp] = tile.cls[tid];
+        }
+        if (rank == 0) {
+          keep[pos] = r;
+          atomicOr(&keep_bits[r >> 5], 1u << (r & 31));
+        }
       }
     }
     __syncthreads();
     NMS_ACC(t_walk, t_mark);
   }
   __syncthreads();
+  if (kCl > 1) {
+    cg::this_cluster().sync();                    // no CTA leaves while a peer may still store into its buffers
+    if (rank != 0) return;
+  }
   const int kept = sh.kept;
   NMS_TRACE(3);
   if (p.trace != nullptr && tid == 0) {
-    p.trace[static_cast<size_t>(blockIdx.x) * 16 + 9] = t_sweep;
-    p.trace[static_cast<size_t>(blockIdx.x) * 16 + 10] = t_matrix;
-    p.trace[static_cast<size_t>(blockIdx.x) * 16 + 11] = t_walk;
+    p.trace[trace_slot * 16 + 9] = t_sweep;
+    p.trace[trace_slot * 16 + 10] = t_matrix;
+    p.trace[trace_slot * 16 + 11] = t_walk;
   }
   if (tid == 0) {
     if (p.keep_cnt) p.keep_cnt[n] = kept;
@@ -621,6 +662,8 @@ template <bool kPerClass>
 __global__ void __launch_bounds__(kSmallThreads, 3) nms_small_kernel(const NmsParams p, int32_t* __restrict__ large) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmallShared& sh = *reinterpret_cast<SmallShared*>(smem_raw);
+  const bool trace_on = true;
+  const size_t trace_slot = blockIdx.x;
   uint32_t* keep_bits = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(SmallShared) + 15) & ~static_cast<size_t>(15)));   // P bits
   const int n = blockIdx.x, P = p.P, row = 4 + p.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -979,8 +1022,8 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   nms_ws_layout(N, P, ws, &w);
   const int row = 4 + C;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_score_kernel), 96 * 1024, fn)) return e;
-  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel<false>), 227 * 1024, fn)) return e;
-  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel<true>), 227 * 1024, fn)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel<false, kNmsCluster>), 227 * 1024, fn)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel<true, kNmsCluster>), 227 * 1024, fn)) return e;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel<false>), 100 * 1024, fn)) return e;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel<true>), 100 * 1024, fn)) return e;
   NmsParams p;
@@ -996,17 +1039,27 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
 
   // Launch helper.  With `pdl` the grid may be scheduled while its predecessor in the stream is still running
   // (programmatic dependent launch); kernels that consume the predecessor's results block in griddepcontrol.wait.
+  int cluster_dim = 1;                 // set before launching a clustered kernel
   auto launch = [&](auto kernel, unsigned grid, int threads, size_t dyn_smem, bool pdl, auto... args) -> int {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = dyn_smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (cluster_dim > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = static_cast<unsigned>(cluster_dim); attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
     if (e != cudaSuccess) { set_error("%s: launch: %s", fn, cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
     return 0;
@@ -1045,8 +1098,9 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
                             : launch(nms_small_kernel<false>, static_cast<unsigned>(nk), kSmallThreads, small_smem, true, pk, w.large + n0)) return e;
     }
   }
-  if (per_class) return launch(nms_kernel<true>, static_cast<unsigned>(N), kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
-  return launch(nms_kernel<false>, static_cast<unsigned>(N), kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
+  cluster_dim = kNmsCluster;           // dense images: a cluster of CTAs each (images already done by nms_small return at once)
+  if (per_class) return launch(nms_kernel<true, kNmsCluster>, static_cast<unsigned>(N) * kNmsCluster, kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
+  return launch(nms_kernel<false, kNmsCluster>, static_cast<unsigned>(N) * kNmsCluster, kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
 }
 
 }  // namespace ssdh
