@@ -195,7 +195,7 @@ constexpr int kMaxRounds = 10;                 // candidates per thread in the s
 
 struct NmsParams {
   float* outputs;
-  int P, C;
+  int N, P, C;
   const float* cand_key;      // [N, P]
   const uint8_t* cand_cls;    // [N, P]
   ThrBand band;
@@ -230,6 +230,7 @@ struct NmsShared {
   int part[4][256];
   int digit_base[256];
   int n_cand, kept, uniform_digit, stop, odd_kept;
+  uint32_t todo[64];                 // which of this cluster's images (cluster_id + k * n_clusters) are left to this kernel
 };
 
 // Debug stamps (ssdh_debug_set_nms_trace): [image][16] SM clocks.
@@ -243,12 +244,12 @@ struct NmsShared {
 template <bool kPerClass, int kCl>
 __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, const int32_t* __restrict__ large) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = blockIdx.x / kCl, P = p.P, row = 4 + p.C;
+  const int P = p.P, row = 4 + p.C;
   const int rank = kCl > 1 ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
+  const int cluster_id = blockIdx.x / kCl, n_clusters = gridDim.x / kCl;
   const bool trace_on = rank == 0;
-  const size_t trace_slot = static_cast<size_t>(n);
+  size_t trace_slot = 0;
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (large != nullptr && large[n] == 0) return;          // already handled by nms_small_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
@@ -273,12 +274,27 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
   const size_t sort_bytes = Pp * (4 + 4 + 2 + 2) + kNmsWarps * 256 * 2, kept_bytes = Pp * (16 + 4 + 1);
   NmsTile& tile = *reinterpret_cast<NmsTile*>(region + (((sort_bytes > kept_bytes ? sort_bytes : kept_bytes) + 15) & ~static_cast<size_t>(15)));
 
+  // The grid is a few dozen clusters, each walking over the images cluster_id, cluster_id + n_clusters, ...; the flags of
+  // those images (1 = too many candidates for nms_small_kernel, left to this kernel) are fetched in one parallel pass.
+  const int mine = p.N > cluster_id ? (p.N - cluster_id + n_clusters - 1) / n_clusters : 0;      // <= 2048 (host check)
+  for (int k0 = 0; k0 < mine; k0 += kNmsThreads) {
+    const int k = k0 + tid;
+    const bool todo = k < mine && (large == nullptr || large[cluster_id + k * n_clusters] != 0);
+    const uint32_t word = __ballot_sync(0xffffffffu, todo);
+    if (lane == 0) sh.todo[(k0 >> 5) + warp] = word;
+  }
+  __syncthreads();
+  for (int k = 0; k < mine; ++k) {
+  if (!((sh.todo[k >> 5] >> (k & 31)) & 1u)) continue;      // uniform for the whole cluster
+  const int n = cluster_id + k * n_clusters;
+  trace_slot = static_cast<size_t>(n);
   const float* key_in = p.cand_key + static_cast<size_t>(n) * P;
   const uint8_t* cls_in = p.cand_cls + static_cast<size_t>(n) * P;
   int32_t* order = p.order + static_cast<size_t>(n) * P;
   int32_t* keep = p.keep + static_cast<size_t>(n) * P;
   float* img = p.outputs + static_cast<size_t>(n) * P * row;
 
+  __syncthreads();                                          // the previous image of this CTA is finished with shared memory
   if (tid == 0) { sh.n_cand = 0; sh.kept = 0; sh.stop = 0; sh.odd_kept = 0; }
   NMS_TRACE(0);
   for (int i = tid; i < bit_words; i += kNmsThreads) keep_bits[i] = 0u;
@@ -593,10 +609,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
     NMS_ACC(t_walk, t_mark);
   }
   __syncthreads();
-  if (kCl > 1) {
-    cg::this_cluster().sync();                    // no CTA leaves while a peer may still store into its buffers
-    if (rank != 0) return;
-  }
+  if (kCl > 1) cg::this_cluster().sync();         // no CTA moves on while a peer may still store into its buffers
+  if (rank != 0) continue;                        // CTA 0 owns the global writes of the image
   const int kept = sh.kept;
   NMS_TRACE(3);
   if (p.trace != nullptr && tid == 0) {
@@ -623,6 +637,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       for (int c = lane; c < p.C; c += 32) dst[c] = 0.0f;
     }
   }
+  }   // images of this cluster
 }
 
 
@@ -1013,6 +1028,7 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
                    int per_class, int32_t* order, int32_t* order_cnt, int32_t* keep, int32_t* keep_cnt, void* ws,
                    size_t ws_bytes, cudaStream_t st, bool fused, const char* fn) {
   if (!outputs || N <= 0 || P <= 0 || C <= 0 || (fused && !priors)) { set_error("%s: NULL pointer or non-positive dimension", fn); return SSDH_E_ARG; }
+  if (N > 65535) { set_error("%s: N <= 65535 per call", fn); return SSDH_E_LIMIT; }
   if (C > kMaxClasses || P > kMaxRounds * kNmsThreads) { set_error("%s: limits are C <= %d, P <= %d", fn, kMaxClasses, kMaxRounds * kNmsThreads); return SSDH_E_LIMIT; }
   const size_t smem = nms_smem_bytes(P);
   if (smem > 227 * 1024) { set_error("%s: P=%d needs %zu bytes of shared memory", fn, P, smem); return SSDH_E_LIMIT; }
@@ -1027,7 +1043,7 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel<false>), 100 * 1024, fn)) return e;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel<true>), 100 * 1024, fn)) return e;
   NmsParams p;
-  p.outputs = outputs; p.P = P; p.C = C;
+  p.outputs = outputs; p.N = N; p.P = P; p.C = C;
   p.cand_key = w.cand_key; p.cand_cls = w.cand_cls;
   p.band = make_band(iou_thr);
   p.score_thr = score_thr; p.top_k = top_k; p.per_class = per_class; p.scatter = fused ? 1 : 0;
@@ -1098,9 +1114,10 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
                             : launch(nms_small_kernel<false>, static_cast<unsigned>(nk), kSmallThreads, small_smem, true, pk, w.large + n0)) return e;
     }
   }
-  cluster_dim = kNmsCluster;           // dense images: a cluster of CTAs each (images already done by nms_small return at once)
-  if (per_class) return launch(nms_kernel<true, kNmsCluster>, static_cast<unsigned>(N) * kNmsCluster, kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
-  return launch(nms_kernel<false, kNmsCluster>, static_cast<unsigned>(N) * kNmsCluster, kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
+  cluster_dim = kNmsCluster;           // dense images: a cluster of CTAs each; 36 clusters (144 of the 148 SMs) walk over the batch
+  const int dense_clusters = N < 36 ? N : 36;
+  if (per_class) return launch(nms_kernel<true, kNmsCluster>, static_cast<unsigned>(dense_clusters) * kNmsCluster, kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
+  return launch(nms_kernel<false, kNmsCluster>, static_cast<unsigned>(dense_clusters) * kNmsCluster, kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
 }
 
 }  // namespace ssdh
