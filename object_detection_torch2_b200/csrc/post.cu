@@ -84,7 +84,7 @@ iou_kernel(const float* __restrict__ t, int t_stride, int T, const float* __rest
 // Writes decoded boxes, ZERO score columns (the NMS kernel scatters the kept scores back) and the
 // per-row candidate key / class used by the sort.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTileRows = 256;
+constexpr int kTileRows = 128;
 
 __global__ void __launch_bounds__(kTileRows)
 decode_score_kernel(float* __restrict__ outputs, const float4* __restrict__ priors, int P, int C, size_t total_rows,
