@@ -279,3 +279,24 @@ def test_compact_ground_truth_round_trip_equals_pad_sequence():
     # without lengths every row is taken as real: zero rows then carry the void label like any other row would
     full = ops.expand_targets(compact.to(DEV), None, 21).cpu()
     assert torch.equal(full[2], want[2]) and float(full[1, 0, 4]) == 1.0
+
+
+@pytest.mark.gpu
+def test_dense_batch_matches_per_image_calls(priors_gpu):
+    """More dense images than clusters: every cluster of the dense NMS kernel walks over several images (and skips the
+    trained-like ones nms_small has already settled).  Each image must come out exactly as when it is processed alone."""
+    n = 44
+    o = synth.make_outputs(n, 131, "D1")
+    sparse = synth.make_outputs(n, 132, "D2")
+    mix = [3, 17, 40]                                        # a few images nms_small handles, in between the dense ones
+    o[mix] = sparse[mix]
+    batch = o.to(DEV)
+    res = ops.postprocess_(batch, priors_gpu, iou_thresh=0.45, want_lists=True)
+    assert int((res.order_cnt > 512).sum()) == n - len(mix)
+    for i in (0, 3, 16, 17, 36, 37, 43):
+        single = o[i:i + 1].to(DEV)
+        r1 = ops.postprocess_(single, priors_gpu, iou_thresh=0.45, want_lists=True)
+        o_b, k_b = lists(res, i)
+        o_s, k_s = lists(r1, 0)
+        assert torch.equal(o_b, o_s) and torch.equal(k_b, k_s), i
+        assert torch.equal(batch[i], single[0]), i
