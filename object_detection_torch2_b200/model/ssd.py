@@ -110,9 +110,11 @@ class SSD(nn.Module):
                 levels.append(self.detectors[det](x))
         if not levels:
             return x.new_empty((n, 0, width))
-        if levels[0].is_cuda and levels[0].dtype == torch.float32:
+        if levels[0].is_cuda:
             return ops.pack_head(levels, width)          # one pass: NCHW detector outputs -> (N, 8732, 4 + C) rows
-        return torch.cat([t.permute(0, 2, 3, 1).reshape(n, -1, width) for t in levels], dim=1)    # reference tail (CPU / other dtypes)
+        # the trunk is stock torch and also runs on the host (e.g. to inspect shapes); there the tail is the reference's own
+        # permute / reshape / cat (ssd.py:103-104).  The hot-path entry points (loss, decode, score, NMS, eval) have no host path.
+        return torch.cat([t.permute(0, 2, 3, 1).reshape(n, -1, width) for t in levels], dim=1)
 
     def _get_default_bboxes(self) -> torch.Tensor:
         """(8732, 4) priors; kernel ssdh_default_boxes, bit-identical to reference ssd.py:108-133."""
