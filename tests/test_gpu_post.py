@@ -300,3 +300,28 @@ def test_dense_batch_matches_per_image_calls(priors_gpu):
         o_s, k_s = lists(r1, 0)
         assert torch.equal(o_b, o_s) and torch.equal(k_b, k_s), i
         assert torch.equal(batch[i], single[0]), i
+
+
+@pytest.mark.gpu
+def test_ssd_forward_uses_the_head_producer(priors_cpu):
+    """SSD.forward (reference ssd.py:96-104): (N, 3, 300, 300) -> (N, 8732, 25) through ssdh_pack_head, identical in
+    value and gradient to the reference's permute / reshape / cat tail over the same detector outputs."""
+    from object_detection_torch2_b200.model import SSD
+    torch.manual_seed(0)
+    net = SSD(num_classes=21).to(DEV).eval()
+    assert torch.equal(net.default_bboxes, priors_cpu)
+    x = torch.rand(2, 3, 300, 300, device=DEV)
+    y = net(x)
+    assert y.shape == (2, 8732, 25)
+    # the same network with the reference tail
+    levels, h = [], net.normalize(x)
+    for name, layer in net.features.items():
+        h = layer(h)
+        if name.startswith("act") and "det" + name[3:] in net.detectors:
+            levels.append(net.detectors["det" + name[3:]](h))
+    want = _reference_tail(levels, 25)
+    assert torch.equal(y, want)
+    w = torch.randn_like(y)
+    g1 = torch.autograd.grad((y * w).sum(), net.detectors["det_4_3"].weight, retain_graph=True)[0]
+    g2 = torch.autograd.grad((want * w).sum(), net.detectors["det_4_3"].weight)[0]
+    torch.testing.assert_close(g1, g2, rtol=1e-5, atol=1e-6)
