@@ -325,3 +325,22 @@ def test_ssd_forward_uses_the_head_producer(priors_cpu):
     g1 = torch.autograd.grad((y * w).sum(), net.detectors["det_4_3"].weight, retain_graph=True)[0]
     g2 = torch.autograd.grad((want * w).sum(), net.detectors["det_4_3"].weight)[0]
     torch.testing.assert_close(g1, g2, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_training_step_through_the_whole_module():
+    """The reference's training step (src/train.py:118-121): forward, SSD.loss with kwargs, backward -- gradients reach
+    the trainable layers through ssdh_multibox_loss (fused backward) and ssdh_unpack_head."""
+    from object_detection_torch2_b200.model import SSD
+    torch.manual_seed(1)
+    net = SSD(num_classes=21).to(DEV).train()
+    images = torch.rand(2, 3, 300, 300, device=DEV)
+    targets = synth.make_targets(2, 141, 5).to(DEV)
+    outputs = net(images)
+    loss = net.loss(outputs=outputs, targets=targets, default_bboxes=net.default_bboxes.to(DEV))
+    assert loss.dim() == 0 and torch.isfinite(loss)
+    loss.backward()
+    g = net.detectors["det_7_1"].weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0.0
+    assert net.features["conv_1_1"].weight.grad is None            # the VGG trunk is frozen (reference ssd.py:31-32)
+    assert list(net.train_params())                                 # optimiser parameter groups as in the reference
