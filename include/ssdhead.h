@@ -15,7 +15,8 @@
  *   - return value: 0 = OK, <0 = SSDH_E_* argument error, >0 = cudaError_t of a failed launch;
  *     ssdh_last_error() returns a thread-local message for the last non-zero return;
  *   - limits: 1 <= C <= 64 classes (incl. void at index 0), G <= 64 ground-truth rows per image,
- *     one image's [P, 4+C] slab must fit the cluster's shared memory (P*(4+C)*4 <= ~1.7 MB).
+ *     one image's [P, 4+C] slab must fit the cluster's shared memory (P*(4+C)*4 <= ~1.7 MB), P <= 65535;
+ *     NMS / post-processing: N <= 65535 images per call, P <= 10240 priors per image.
  */
 #ifndef SSDHEAD_H_
 #define SSDHEAD_H_
