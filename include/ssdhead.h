@@ -108,9 +108,15 @@ SSDH_API int ssdh_multibox_loss(const float* outputs, const float* targets, cons
                        float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
                        void* ws, size_t ws_bytes, ssdh_stream_t stream);
 
-/* Same as ssdh_multibox_loss, plus software pipelining across micro-batches: once this batch's slabs are on chip (HBM is
- * then idle until the gradient is written) every CTA asks the L2 for the blocks it will read from next_outputs /
- * next_targets (same shapes; either may be NULL) in the NEXT call.  Pure hint: no data is changed. */
+/* Same as ssdh_multibox_loss for callers that run it back to back on buffers that are ALREADY COMPLETE (a training loop
+ * over micro-batches staged earlier, gradient accumulation, a benchmark): by calling this entry point the caller vouches
+ * that outputs / targets / priors were not written by the kernel that precedes this call in the stream.  That allows
+ *   - programmatic dependent launch with early reads: the grid loads, matches and selects under the previous grid's tail
+ *     and only waits for it before its first global write (ssdh_multibox_loss waits before its first global READ, because
+ *     its predecessor is normally the producer of `outputs`);
+ *   - software pipelining across micro-batches: once this batch's slabs are on chip (HBM is then idle until the gradient
+ *     is written) every CTA asks the L2 for the blocks it will read from next_outputs / next_targets (same shapes; either
+ *     may be NULL) in the NEXT call.  Pure hint: no data is changed. */
 SSDH_API int ssdh_multibox_loss_pipelined(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
                        float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
                        void* ws, size_t ws_bytes, ssdh_stream_t stream, const float* next_outputs, const float* next_targets);
@@ -181,6 +187,19 @@ SSDH_API int ssdh_gather_detections(const float* outputs, const int32_t* keep, c
 SSDH_API size_t ssdh_eval_workspace_bytes(int N, int P, int C, int G);
 SSDH_API int ssdh_eval_accumulate(const float* outputs, const float* gts, int N, int P, int C, int G, float iou_thr,
                          int64_t* tallies, uint8_t* tp_flags, void* ws, size_t ws_bytes, ssdh_stream_t stream);
+
+/* Same tallies, fed from the kept lists the NMS pass has just produced (keep [N, P] i32 / keep_cnt [N] of ssdh_nms /
+ * ssdh_postprocess) instead of re-scanning the dense tensor: per image only the kept rows are read (a few hundred x
+ * (4+C)*4 bytes instead of the whole P*(4+C)*4 slab), which is what makes decode + NMS + tallies cost 2*S + O(kept) per
+ * image rather than 3*S.  Rows must be calc_score rows (one positive class column at most). */
+SSDH_API int ssdh_eval_accumulate_kept(const float* outputs, const int32_t* keep, const int32_t* keep_cnt, const float* gts,
+                              int N, int P, int C, int G, float iou_thr, int64_t* tallies, uint8_t* tp_flags,
+                              void* ws, size_t ws_bytes, ssdh_stream_t stream);
+
+/* Reads back the status word of an eval workspace (host out-param): 0 = fine, 1 = some image handed ssdh_eval_accumulate
+ * more than P positive score entries (rows with several positive classes) and detections were dropped.  The ONLY
+ * entry point that synchronises (4 bytes device -> host on `stream`); call it once after the last batch. */
+SSDH_API int ssdh_eval_status(const void* ws, int* status_host, ssdh_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,8 @@ struct EvalParams {
   unsigned long long* tallies;   // [C-1, 3]
   uint8_t* tp_flags;             // [N, P] or NULL
   int* status;                   // workspace: set to 1 if an image had more than P detections
+  const int32_t* keep;           // [N, P] kept rows in score order (ssdh_nms / ssdh_postprocess), or NULL: scan the slab
+  const int32_t* keep_cnt;       // [N]
 };
 
 struct Det {          // 4 bytes: the score is re-read from the slab when a claim is made (keeps five images per SM)
@@ -29,6 +31,10 @@ struct Det {          // 4 bytes: the score is re-read from the slab when a clai
   uint8_t best_g;   // 255 = no valid claim
 };
 
+// kKept = false: the detections are found by scanning the whole [P, 4+C] slab (any rows, several positive classes per row
+// allowed): S bytes per image.  kKept = true: the detections ARE the kept list the NMS pass has just written -- only those
+// rows are touched (a few hundred x 100 bytes per image instead of 873 KB); rows must carry one positive class at most.
+template <bool kKept>
 __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = blockIdx.x, P = p.P, C = p.C, G = p.G, row = 4 + C, NC = C - 1;
@@ -79,6 +85,7 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams p) 
   // load when the slab allows).  The decoded box columns are positive in every row, so the column of each element is
   // tracked incrementally (no division) and only score columns are examined; after NMS a few hundred entries per image
   // are positive and only those pay for the row / column split.
+  if (!kKept) {
   const int total = P * row;
   auto take = [&](int i, float v) {
     if (!(v > 0.0f)) return;
@@ -122,6 +129,23 @@ __global__ void __launch_bounds__(kEvalThreads) eval_kernel(const EvalParams p) 
     for (int i = tid; i < total; i += kEvalThreads) {
       const float v = img[i];
       if (v > 0.0f && i % row >= 5) take(i, v);
+    }
+  }
+  } else {
+    // kept list -> detections: thread per kept row; its class is the (single) positive score column
+    const int K = min(p.keep_cnt[n], P);
+    const int32_t* kp = p.keep + static_cast<size_t>(n) * P;
+    for (int i = tid; i < K; i += kEvalThreads) {
+      const int r = kp[i];
+      const float* sc = img + static_cast<size_t>(r) * row + 5;
+      int cls = -1;
+      for (int c = 0; c < NC; ++c)
+        if (cls < 0 && sc[c] > 0.0f) cls = c;
+      if (cls < 0) continue;                       // a kept row always has a positive score; tolerate foreign lists
+      const int slot = atomicAdd(n_det, 1);
+      Det d;
+      d.row = static_cast<uint16_t>(r); d.cls = static_cast<uint8_t>(cls); d.best_g = 255;
+      dets[slot] = d;
     }
   }
   __syncthreads();
@@ -187,20 +211,44 @@ extern "C" size_t ssdh_eval_workspace_bytes(int N, int P, int C, int G) {
   return 256;
 }
 
-extern "C" int ssdh_eval_accumulate(const float* outputs, const float* gts, int N, int P, int C, int G, float iou_thr,
-                                    int64_t* tallies, uint8_t* tp_flags, void* ws, size_t ws_bytes, ssdh_stream_t stream) {
+static int eval_impl(const float* outputs, const int32_t* keep, const int32_t* keep_cnt, const float* gts, int N, int P, int C, int G,
+                     float iou_thr, int64_t* tallies, uint8_t* tp_flags, void* ws, size_t ws_bytes, ssdh_stream_t stream) {
   if (!outputs || !tallies || N <= 0 || P <= 0 || C <= 1 || G < 0 || (G > 0 && !gts)) { set_error("ssdh_eval_accumulate: bad argument"); return SSDH_E_ARG; }
   if (C > kMaxClasses || G > kMaxGT || P > 65535) { set_error("ssdh_eval_accumulate: limits are C <= %d, G <= %d, P <= 65535", kMaxClasses, kMaxGT); return SSDH_E_LIMIT; }
   if (!ws || ws_bytes < ssdh_eval_workspace_bytes(N, P, C, G)) { set_error("ssdh_eval_accumulate: workspace too small"); return SSDH_E_WORKSPACE; }
   const size_t smem = eval_smem_bytes(P, C, G);
   if (smem > 227 * 1024) { set_error("ssdh_eval_accumulate: needs %zu bytes of shared memory", smem); return SSDH_E_LIMIT; }
-  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(eval_kernel), 227 * 1024, "ssdh_eval_accumulate")) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(eval_kernel<false>), 227 * 1024, "ssdh_eval_accumulate")) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(eval_kernel<true>), 227 * 1024, "ssdh_eval_accumulate")) return e;
   EvalParams p;
   p.outputs = outputs; p.gts = gts; p.P = P; p.C = C; p.G = G;
   p.band = make_band(iou_thr);
   p.tallies = reinterpret_cast<unsigned long long*>(tallies);
   p.tp_flags = tp_flags;
   p.status = reinterpret_cast<int*>(ws);
-  eval_kernel<<<N, kEvalThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  p.keep = keep; p.keep_cnt = keep_cnt;
+  if (keep) eval_kernel<true><<<N, kEvalThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  else eval_kernel<false><<<N, kEvalThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
   return cuda_status("ssdh_eval_accumulate");
+}
+
+extern "C" int ssdh_eval_accumulate(const float* outputs, const float* gts, int N, int P, int C, int G, float iou_thr,
+                                    int64_t* tallies, uint8_t* tp_flags, void* ws, size_t ws_bytes, ssdh_stream_t stream) {
+  return eval_impl(outputs, nullptr, nullptr, gts, N, P, C, G, iou_thr, tallies, tp_flags, ws, ws_bytes, stream);
+}
+
+extern "C" int ssdh_eval_accumulate_kept(const float* outputs, const int32_t* keep, const int32_t* keep_cnt, const float* gts,
+                                         int N, int P, int C, int G, float iou_thr, int64_t* tallies, uint8_t* tp_flags,
+                                         void* ws, size_t ws_bytes, ssdh_stream_t stream) {
+  if (!keep || !keep_cnt) { set_error("ssdh_eval_accumulate_kept: keep / keep_cnt are required"); return SSDH_E_ARG; }
+  return eval_impl(outputs, keep, keep_cnt, gts, N, P, C, G, iou_thr, tallies, tp_flags, ws, ws_bytes, stream);
+}
+
+extern "C" int ssdh_eval_status(const void* ws, int* status_host, ssdh_stream_t stream) {
+  if (!ws || !status_host) { set_error("ssdh_eval_status: NULL pointer"); return SSDH_E_ARG; }
+  // the one synchronising entry point of the library, deliberately separate from the launches: 4 bytes D2H
+  cudaError_t e = cudaMemcpyAsync(status_host, ws, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) { set_error("ssdh_eval_status: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
+  return 0;
 }

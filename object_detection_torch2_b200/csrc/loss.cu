@@ -65,6 +65,8 @@ struct LossParams {
   int rows_per_cta;       // shared-memory rows reserved per CTA (multiple of kChunkRows)
   int n_chunks;           // ceil(P / kChunkRows)
   int bulk;               // 1: every block is 16-byte aligned/sized -> TMA path
+  int early_inputs;       // 1: outputs / targets / priors were complete before the PREVIOUS kernel of the stream started, so they
+                          //    may be read under that kernel's tail (programmatic dependent launch); 0: wait for it first
   unsigned long long* trace;   // debug: [grid][kTracePoints] SM clock stamps (NULL in production)
 };
 
@@ -296,6 +298,10 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   // everything that only reads its own inputs (load, match, CE, selection) under this grid's tail; it blocks at
   // griddepcontrol.wait below, before its first global write (workspace, loss, stats, gradient).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // The kernel in front of us in the stream is normally the PRODUCER of outputs / targets (the head's last kernel, a copy,
+  // ssdh_expand_targets ...): its writes are only guaranteed visible after griddepcontrol.wait, so unless the caller vouches
+  // for the inputs (ssdh_multibox_loss_pipelined) nothing is read from global memory before this point.
+  if (!p.early_inputs) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- setup ------------------------------------------------------------------------------------
   trace_point_t<kTrace>(p, 0);
@@ -1037,7 +1043,8 @@ extern "C" size_t ssdh_multibox_loss_workspace_bytes(int N, int P, int C, int G)
 
 static int multibox_loss_impl(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
                               float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
-                              void* ws, size_t ws_bytes, ssdh_stream_t stream, const float* next_outputs, const float* next_targets) {
+                              void* ws, size_t ws_bytes, ssdh_stream_t stream, const float* next_outputs, const float* next_targets,
+                              bool inputs_stable) {
   if (!outputs || !priors || !loss || N <= 0 || P <= 0 || C <= 0 || G < 0 || n_global <= 0 || (G > 0 && !targets)) {
     set_error("ssdh_multibox_loss: NULL pointer or non-positive dimension");
     return SSDH_E_ARG;
@@ -1071,6 +1078,7 @@ static int multibox_loss_impl(const float* outputs, const float* targets, const 
   // TMA bulk copies need 16-byte aligned addresses and sizes for every (image, CTA, slot) chunk.
   const bool sizes_ok = (static_cast<long long>(P) * row) % 4 == 0;     // full blocks are 32 rows; only the tail block can be odd
   p.bulk = sizes_ok && aligned16(outputs) && (grad == nullptr || aligned16(grad));
+  p.early_inputs = inputs_stable ? 1 : 0;
   p.trace = g_loss_trace;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (C == 21) return launch_loss_shape<21>(p, shape, st);
@@ -1080,14 +1088,14 @@ static int multibox_loss_impl(const float* outputs, const float* targets, const 
 extern "C" int ssdh_multibox_loss(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
                                   float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
                                   void* ws, size_t ws_bytes, ssdh_stream_t stream) {
-  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, nullptr, nullptr);
+  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, nullptr, nullptr, false);
 }
 
 extern "C" int ssdh_multibox_loss_pipelined(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
                                             float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
                                             void* ws, size_t ws_bytes, ssdh_stream_t stream, const float* next_outputs,
                                             const float* next_targets) {
-  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, next_outputs, next_targets);
+  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, next_outputs, next_targets, true);
 }
 
 // Debug hook (not part of the public header): device buffer of [N * 8][16] u64 phase stamps, or NULL to disable.

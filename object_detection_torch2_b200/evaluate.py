@@ -18,9 +18,11 @@ def get_order(t: torch.Tensor, class_id: int) -> torch.Tensor:
 
 
 def accumulate(outputs: torch.Tensor, gts: torch.Tensor, tallies: Optional[torch.Tensor] = None, iou_thresh: float = 0.5,
-               want_flags: bool = False):
-    """One batch of src/evaluate.py:132-151: adds {TP, detections, ground truths} per class to ``tallies``."""
-    return ops.eval_accumulate(outputs, gts, tallies, iou_thresh, want_flags)
+               want_flags: bool = False, keep: Optional[torch.Tensor] = None, keep_cnt: Optional[torch.Tensor] = None,
+               check_status: bool = True):
+    """One batch of src/evaluate.py:132-151: adds {TP, detections, ground truths} per class to ``tallies``.
+    ``keep`` / ``keep_cnt`` (from ``ops.postprocess_(..., want_lists=True)``) let the kernel read only the kept rows."""
+    return ops.eval_accumulate(outputs, gts, tallies, iou_thresh, want_flags, keep, keep_cnt, check_status)
 
 
 def average_precision_from_tallies(tallies: torch.Tensor) -> torch.Tensor:
@@ -85,9 +87,11 @@ class DetectionEvaluator:
         self.tallies: Optional[torch.Tensor] = None
         self.cls, self.score, self.tp = [], [], []
 
-    def update(self, outputs: torch.Tensor, gts: torch.Tensor) -> None:
-        """``outputs`` (N, P, 4+C) after NMS, ``gts`` (N, G, 4+C)."""
-        self.tallies, flags = ops.eval_accumulate(outputs, gts, self.tallies, self.iou_thresh, want_flags=True)
+    def update(self, outputs: torch.Tensor, gts: torch.Tensor, keep: Optional[torch.Tensor] = None,
+               keep_cnt: Optional[torch.Tensor] = None) -> None:
+        """``outputs`` (N, P, 4+C) after NMS, ``gts`` (N, G, 4+C); optionally the kept lists of the NMS pass."""
+        self.tallies, flags = ops.eval_accumulate(outputs, gts, self.tallies, self.iou_thresh, want_flags=True, keep=keep,
+                                                  keep_cnt=keep_cnt)
         rows = flags != 255
         scores, cls = outputs[:, :, 5:][rows].max(dim=1)
         self.cls.append(cls.to(torch.int32))

@@ -97,7 +97,7 @@ class SSD(nn.Module):
         """(N, 3, 300, 300) -> (N, 8732, 4 + C), rows level-major then (cell row, cell col, anchor).
 
         The reference looks detectors up with the activation's name and therefore finds none (ssd.py:102, SURVEY
-        section 0 item 3); the evidently intended ``act_*`` -> ``det_*`` pairing is used here.  On the GPU the six detector outputs go through
+        section 0 item 3); the evidently intended ``act_*`` -> ``det_*`` pairing is used here.  The six detector outputs go through
         ``ssdh_pack_head``: permute + reshape + cat (ssd.py:103-104) as one pass over the data."""
         n = x.size(0)
         width = self.num_classes + 4
@@ -110,11 +110,9 @@ class SSD(nn.Module):
                 levels.append(self.detectors[det](x))
         if not levels:
             return x.new_empty((n, 0, width))
-        if levels[0].is_cuda:
-            return ops.pack_head(levels, width)          # one pass: NCHW detector outputs -> (N, 8732, 4 + C) rows
-        # the trunk is stock torch and also runs on the host (e.g. to inspect shapes); there the tail is the reference's own
-        # permute / reshape / cat (ssd.py:103-104).  The hot-path entry points (loss, decode, score, NMS, eval) have no host path.
-        return torch.cat([t.permute(0, 2, 3, 1).reshape(n, -1, width) for t in levels], dim=1)
+        # no host path: the tail is ssdh_pack_head (permute + reshape + cat of ssd.py:103-104 as one pass) and raises on CPU
+        # tensors like every other entry point of the head
+        return ops.pack_head(levels, width)
 
     def _get_default_bboxes(self) -> torch.Tensor:
         """(8732, 4) priors; kernel ssdh_default_boxes, bit-identical to reference ssd.py:108-133."""

@@ -181,12 +181,15 @@ def multibox_loss_raw(outputs: torch.Tensor, targets: torch.Tensor, priors: torc
                       n_global: Optional[int] = None, want_grad: bool = True, want_stats: bool = False,
                       loss_out: Optional[torch.Tensor] = None, grad_out: Optional[torch.Tensor] = None,
                       stats_out: Optional[torch.Tensor] = None, next_outputs: Optional[torch.Tensor] = None,
-                      next_targets: Optional[torch.Tensor] = None):
+                      next_targets: Optional[torch.Tensor] = None, inputs_stable: bool = False):
     """One launch: loss (0-d), d loss / d outputs (or None) and per-image stats (uint8 (N, 32) view of ssdh_image_stats, or None).
 
-    Inputs must already be contiguous fp32 CUDA tensors (this is the graph-capturable hot call)."""
+    Inputs must already be contiguous fp32 CUDA tensors (this is the graph-capturable hot call).  ``inputs_stable`` (implied
+    by ``next_outputs`` / ``next_targets``): the caller vouches that the inputs were not written by the kernel that precedes
+    this call in the stream, see ssdh_multibox_loss_pipelined."""
     lib = _lib.load()
     _need_cuda(outputs, targets, priors)
+    _check_loss_args(outputs, targets, priors, next_outputs, next_targets, loss_out, grad_out)
     N, P, row = outputs.shape
     C = row - 4
     G = targets.shape[1]
@@ -204,14 +207,36 @@ def multibox_loss_raw(outputs: torch.Tensor, targets: torch.Tensor, priors: torc
                 float(a), float(threshold), int(n_global or N), loss_out.data_ptr(),
                 _ptr(grad_out) if want_grad else None, _ptr(stats_out) if want_stats else None,
                 ws.data_ptr(), ws.numel(), _stream())
-        if next_outputs is None and next_targets is None:
+        if next_outputs is None and next_targets is None and not inputs_stable:
             check(lib.ssdh_multibox_loss(*args), "ssdh_multibox_loss")
         else:                                   # L2 prefetch of the next micro-batch (same shapes) from inside the kernel
             _need_cuda(next_outputs, next_targets)
-            if next_outputs is not None and next_outputs.shape != outputs.shape:
-                raise ValueError("next_outputs must have the shape of outputs")
             check(lib.ssdh_multibox_loss_pipelined(*args, _ptr(next_outputs), _ptr(next_targets)), "ssdh_multibox_loss_pipelined")
     return loss_out, (grad_out if want_grad else None), (stats_out if want_stats else None)
+
+
+def _check_loss_args(outputs, targets, priors, next_outputs, next_targets, loss_out, grad_out) -> None:
+    """The kernel trusts these shapes: a mismatched class count or stride would make it read out of bounds."""
+    if outputs.dim() != 3 or targets.dim() != 3 or priors.dim() != 2:
+        raise ValueError("multibox_loss: outputs (N, P, 4+C), targets (N, G, 4+C), priors (P, 4) expected")
+    N, P, row = outputs.shape
+    if row < 5:
+        raise ValueError("multibox_loss: outputs rows are [4 offsets, C >= 1 logits]")
+    if targets.shape[0] != N or targets.shape[2] != row:
+        raise ValueError(f"multibox_loss: targets {tuple(targets.shape)} do not match outputs {tuple(outputs.shape)} (need (N, G, {row}))")
+    if tuple(priors.shape) != (P, 4):
+        raise ValueError(f"multibox_loss: priors {tuple(priors.shape)} do not match outputs (need ({P}, 4))")
+    for name, t, shape in (("outputs", outputs, None), ("targets", targets, None), ("priors", priors, None),
+                           ("next_outputs", next_outputs, outputs.shape), ("next_targets", next_targets, targets.shape),
+                           ("grad_out", grad_out, outputs.shape)):
+        if t is None:
+            continue
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.device != outputs.device:
+            raise ValueError(f"multibox_loss: {name} must be a contiguous fp32 tensor on {outputs.device}")
+        if shape is not None and t.shape != shape:
+            raise ValueError(f"multibox_loss: {name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    if loss_out is not None and (loss_out.dtype != torch.float32 or loss_out.numel() != 1 or loss_out.device != outputs.device):
+        raise ValueError("multibox_loss: loss_out must be a one-element fp32 tensor on the device of outputs")
 
 
 def stats_to_numpy(stats: torch.Tensor) -> np.ndarray:
@@ -226,13 +251,21 @@ class _MultiBoxLossFn(torch.autograd.Function):
         want_grad = ctx.needs_input_grad[0]
         loss, grad, _ = multibox_loss_raw(outputs, targets, priors, a, threshold, n_global, want_grad=want_grad)
         ctx.grad = grad
+        ctx.consumed = False
         return loss
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         grad = ctx.grad
         if grad is None:
             return (None,) * 6
+        if ctx.consumed:
+            # the chain-rule factor is applied in place on the gradient the forward launch wrote (no second 28 MB buffer on
+            # the hot path), so that buffer cannot serve a second backward
+            raise RuntimeError("SSD.loss: backward through the fused MultiBox loss a second time (retain_graph=True or several "
+                               "heads over one loss); call loss() again instead -- the gradient buffer was scaled in place")
+        ctx.consumed = True
         lib = _lib.load()
         g = _f32c(g.reshape(1))
         with torch.cuda.device(grad.device):
@@ -426,22 +459,62 @@ def gather_detections(outputs: torch.Tensor, keep: torch.Tensor, keep_cnt: torch
 
 # ------------------------------------------------------------------------------------------------ E1-E2
 def eval_accumulate(outputs: torch.Tensor, gts: torch.Tensor, tallies: Optional[torch.Tensor] = None, iou_thresh: float = 0.5,
-                    want_flags: bool = False):
-    """Adds this batch's {TP, detections, ground truths} per class into ``tallies`` (int64 (C-1, 3))."""
+                    want_flags: bool = False, keep: Optional[torch.Tensor] = None, keep_cnt: Optional[torch.Tensor] = None,
+                    check_status: bool = True):
+    """Adds this batch's {TP, detections, ground truths} per class into ``tallies`` (int64 (C-1, 3)).
+
+    With ``keep`` / ``keep_cnt`` (the lists ``nms_`` / ``postprocess_`` return under ``want_lists=True``) only the kept rows
+    are read instead of the whole tensor.  ``check_status`` reads the kernel's overflow word back after the launch (one
+    4-byte synchronising copy; skipped while a CUDA graph is being captured) and raises if detections were dropped --
+    pass False in a pipelined loop and call ``eval_status`` once at the end."""
     lib = _lib.load()
-    _need_cuda(outputs, gts, tallies)
+    _need_cuda(outputs, gts, tallies, keep, keep_cnt)
     outputs, gts = _f32c(outputs), _f32c(gts)
     N, P, row = outputs.shape
     C = row - 4
     G = gts.shape[1]
     dev = outputs.device
+    if gts.shape[0] != N or gts.shape[2] != row:
+        raise ValueError(f"eval_accumulate: gts {tuple(gts.shape)} do not match outputs {tuple(outputs.shape)}")
+    if (keep is None) != (keep_cnt is None):
+        raise ValueError("eval_accumulate: keep and keep_cnt go together")
+    if keep is not None:
+        if keep.dtype != torch.int32 or keep_cnt.dtype != torch.int32 or tuple(keep.shape) != (N, P) or keep_cnt.numel() != N:
+            raise ValueError("eval_accumulate: keep (N, P) int32 and keep_cnt (N,) int32 expected")
+        keep, keep_cnt = keep.contiguous(), keep_cnt.contiguous()
     if tallies is None:
         tallies = torch.zeros(C - 1, 3, dtype=torch.int64, device=dev)
     flags = torch.empty(N, P, dtype=torch.uint8, device=dev) if want_flags else None
     if N > 0:
         with torch.cuda.device(dev):
             ws = _workspace("eval", lib.ssdh_eval_workspace_bytes(N, P, C, G), dev, zero=True)
-            check(lib.ssdh_eval_accumulate(outputs.data_ptr(), gts.data_ptr() if G > 0 else None, N, P, C, G, float(iou_thresh),
-                                           tallies.data_ptr(), _ptr(flags), ws.data_ptr(), ws.numel(), _stream()),
-                  "ssdh_eval_accumulate")
+            gptr = gts.data_ptr() if G > 0 else None
+            if keep is None:
+                check(lib.ssdh_eval_accumulate(outputs.data_ptr(), gptr, N, P, C, G, float(iou_thresh),
+                                               tallies.data_ptr(), _ptr(flags), ws.data_ptr(), ws.numel(), _stream()),
+                      "ssdh_eval_accumulate")
+            else:
+                check(lib.ssdh_eval_accumulate_kept(outputs.data_ptr(), keep.data_ptr(), keep_cnt.data_ptr(), gptr, N, P, C, G,
+                                                    float(iou_thresh), tallies.data_ptr(), _ptr(flags), ws.data_ptr(), ws.numel(),
+                                                    _stream()), "ssdh_eval_accumulate_kept")
+        if check_status and keep is None and not torch.cuda.is_current_stream_capturing():
+            eval_status(dev)
     return tallies, flags
+
+
+def eval_status(device) -> None:
+    """Raises if any ``eval_accumulate`` call on the current stream since the last check dropped detections (an image
+    with more than P positive score entries: rows with several positive classes, i.e. input that skipped ``calc_score``)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    key = ("eval", device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ws = _ws_cache.get(key)
+    if ws is None:
+        return
+    status = ctypes.c_int(0)
+    with torch.cuda.device(device):
+        check(lib.ssdh_eval_status(ws.data_ptr(), ctypes.byref(status), _stream()), "ssdh_eval_status")
+        if status.value != 0:
+            ws[:4].zero_()
+            raise _lib.SsdHeadError("ssdh_eval_accumulate: an image had more than P positive score entries (rows with several "
+                                    "positive classes); detections were dropped.  Feed calc_score / postprocess output.")

@@ -90,3 +90,60 @@ def plant_detections(outputs: torch.Tensor, targets: torch.Tensor, priors: torch
                 out[n, r, 4:] = -2.0
                 out[n, r, 4 + label] = 4.0 + 4.0 * float(torch.rand(1, generator=g))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Device-side generators for the large benchmark legs (1024-image and 4952-image configs): the same distributions, drawn
+# with a CUDA generator so that gigabytes of inputs do not have to come through the host.  Deterministic for a given
+# (seed, shape, GPU model, torch build) -- every rank of one box regenerates the same block from the same seed.
+# ---------------------------------------------------------------------------------------------------------------------
+def make_outputs_device(n_images: int, seed: int, dist: str, device, num_priors: int = NUM_PRIORS,
+                        num_classes: int = NUM_CLASSES) -> torch.Tensor:
+    g = torch.Generator(device=device).manual_seed(7919 * seed + 3)
+    x = torch.randn(n_images, num_priors, 4 + num_classes, generator=g, dtype=torch.float32, device=device)
+    if dist == "D2":
+        x[:, :, :4] *= 0.1
+        x[:, :, 4] += 4.0
+    elif dist != "D1":
+        raise ValueError(f"unknown distribution {dist!r}")
+    return x
+
+
+def pad_targets(targets: torch.Tensor, g_rows: int) -> torch.Tensor:
+    """Zero-pad the ground-truth axis to ``g_rows`` rows (padding rows are inert, reference ssd.py:250,269)."""
+    n, g, row = targets.shape
+    if g >= g_rows:
+        return targets
+    return torch.cat([targets, targets.new_zeros(n, g_rows - g, row)], dim=1)
+
+
+def plant_detections_device(outputs: torch.Tensor, targets: torch.Tensor, priors: torch.Tensor, per_gt: int = 2,
+                            chunk: int = 64) -> torch.Tensor:
+    """Vectorised, in-place variant of ``plant_detections`` for tensors that live on the GPU: for every real ground-truth
+    box the ``per_gt`` nearest priors are rewritten so that they decode onto the box (the second one shifted by 4 % of
+    the box size, so the duplicates overlap and NMS / first-claimant bookkeeping have work to do) with a confident logit
+    for its label.  Deterministic (no random numbers)."""
+    N, G = targets.shape[0], targets.shape[1]
+    pr = priors.to(outputs.device)
+    for n0 in range(0, N, chunk):
+        t = targets[n0:n0 + chunk].to(outputs.device)
+        box = t[:, :, :4]                                                   # (n, G, 4)
+        real = (box[:, :, 2] * box[:, :, 3]) > 0
+        d = ((pr[None, None, :, 0] - box[:, :, None, 0]).abs() + (pr[None, None, :, 1] - box[:, :, None, 1]).abs()
+             + (pr[None, None, :, 2] - box[:, :, None, 2]).abs())           # (n, G, P)
+        rows = torch.topk(d, per_gt, dim=2, largest=False).indices          # (n, G, per_gt)
+        label = t[:, :, 4:].argmax(dim=2)                                   # (n, G)
+        for j in range(per_gt):
+            nn, gg = torch.nonzero(real, as_tuple=True)
+            r = rows[nn, gg, j]
+            dp = pr[r]
+            b = box[nn, gg]
+            shift = 0.04 * j
+            vals = torch.full((nn.numel(), outputs.shape[2]), -2.0, device=outputs.device)
+            vals[:, 0] = (b[:, 0] + shift * b[:, 2] - dp[:, 0]) / dp[:, 2]
+            vals[:, 1] = (b[:, 1] - shift * b[:, 3] - dp[:, 1]) / dp[:, 3]
+            vals[:, 2] = torch.log(b[:, 2] / dp[:, 2])
+            vals[:, 3] = torch.log(b[:, 3] / dp[:, 3])
+            vals[torch.arange(nn.numel(), device=outputs.device), 4 + label[nn, gg]] = 6.0 - 1.5 * j
+            outputs[n0 + nn, r] = vals
+    return outputs

@@ -365,3 +365,74 @@ def test_pipelined_call_and_prefetch_are_pure_hints(priors_gpu):
     outs = [ops.multibox_loss_raw(od, td, priors_gpu) for _ in range(8)]
     torch.cuda.synchronize()
     assert all(torch.equal(x[0], base_l) and torch.equal(x[1], base_g) for x in outs)
+
+
+def test_loss_right_behind_its_producers(priors_cpu, priors_gpu):
+    """The kernel in front of the loss in the stream is normally the PRODUCER of its inputs (ssdh_pack_head at the end of
+    SSD.forward, ssdh_expand_targets, a copy): the loss is launched with programmatic stream serialization and must not
+    read `outputs` / `targets` before that producer's writes are visible.  Many back-to-back rounds on the same buffers
+    with changing contents, no synchronisation in between; a stale read shows up as the previous round's loss."""
+    levels_shape = [(38, 4), (19, 6), (10, 6), (5, 6), (3, 4), (1, 4)]
+    N = 8
+    g = torch.Generator().manual_seed(5)
+    rounds = []
+    for r in range(6):
+        lv = [torch.randn(N, a * 25, m, m, generator=g) for m, a in levels_shape]
+        t = synth.make_targets(N, 200 + r, 12)
+        rounds.append((lv, t))
+    # expected values, computed with full synchronisation and freshly allocated tensors
+    want = []
+    for lv, t in rounds:
+        o = torch.cat([x.permute(0, 2, 3, 1).reshape(N, -1, 25) for x in lv], dim=1).to(DEV).contiguous()
+        l, gr, _ = ops.multibox_loss_raw(o, t.to(DEV).contiguous(), priors_gpu)
+        torch.cuda.synchronize()
+        want.append((l.clone(), gr.abs().sum().clone()))
+    # now the pipelined stream: stage -> pack -> expand -> loss, all on one stream, buffers reused every round
+    dev_lv = [torch.empty(N, a * 25, m, m, device=DEV) for m, a in levels_shape]
+    G = max(t.shape[1] for _, t in rounds)
+    compact = torch.empty(N, G, 5, device=DEV)
+    lengths = torch.empty(N, dtype=torch.int32, device=DEV)
+    got = []
+    for rep in range(3):
+        for (lv, t) in rounds:
+            tc = synth.pad_targets(t, G)
+            real = (tc[:, :, 2] * tc[:, :, 3]) > 0
+            comp = torch.cat([tc[:, :, :4], tc[:, :, 4:].argmax(dim=2, keepdim=True).float()], dim=2) * real[:, :, None]
+            for d, s in zip(dev_lv, lv):
+                d.copy_(s.to(DEV))
+            compact.copy_(comp.to(DEV))
+            lengths.copy_(real.sum(dim=1).to(torch.int32).to(DEV))
+            o = ops.pack_head(dev_lv, 25)                       # producer 1: last kernel before the loss is NOT this one ...
+            tg = ops.expand_targets(compact, lengths, 21)       # ... producer 2 is (targets), pack_head two launches back
+            l, gr, _ = ops.multibox_loss_raw(o, tg, priors_gpu)
+            got.append((l, gr.abs().sum()))
+            tg2 = ops.expand_targets(compact, lengths, 21)
+            o2 = ops.pack_head(dev_lv, 25)                      # and the other order: pack_head directly in front of the loss
+            l2, gr2, _ = ops.multibox_loss_raw(o2, tg2, priors_gpu)
+            got.append((l2, gr2.abs().sum()))
+    torch.cuda.synchronize()
+    for i, (l, s) in enumerate(got):
+        wl, ws = want[(i // 2) % len(rounds)]
+        assert torch.equal(l, wl), f"round {i}: loss {float(l)} vs {float(wl)} (stale input read under the producer's tail?)"
+        assert torch.equal(s, ws), f"round {i}: gradient checksum differs"
+
+
+def test_loss_backward_twice_raises_and_args_are_checked(priors_gpu):
+    o, t = synth.make_batch(2, 171, "D2", 4)
+    net = SSD.__new__(SSD)
+    x = o.to(DEV).requires_grad_(True)
+    loss = net.loss(outputs=x, targets=t.to(DEV), default_bboxes=priors_gpu)
+    loss.backward(retain_graph=True)
+    first = x.grad.clone()
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()
+    assert torch.equal(x.grad, first)
+    od, td = o.to(DEV), t.to(DEV)
+    with pytest.raises(ValueError, match="targets"):
+        ops.multibox_loss_raw(od, td[:, :, :24].contiguous(), priors_gpu)            # class count mismatch
+    with pytest.raises(ValueError, match="priors"):
+        ops.multibox_loss_raw(od, td, priors_gpu[:100].contiguous())
+    with pytest.raises(ValueError, match="contiguous"):
+        ops.multibox_loss_raw(od.transpose(0, 1).contiguous().transpose(0, 1), td, priors_gpu)
+    with pytest.raises(ValueError, match="next_targets"):
+        ops.multibox_loss_raw(od, td, priors_gpu, next_outputs=od, next_targets=td[:, :1].contiguous())

@@ -344,3 +344,46 @@ def test_training_step_through_the_whole_module():
     assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0.0
     assert net.features["conv_1_1"].weight.grad is None            # the VGG trunk is frozen (reference ssd.py:31-32)
     assert list(net.train_params())                                 # optimiser parameter groups as in the reference
+
+
+@pytest.mark.gpu
+def test_eval_from_kept_lists_equals_dense_scan(priors_cpu, priors_gpu):
+    """ssdh_eval_accumulate_kept (tallies fed from the NMS pass's kept lists, O(kept) rows per image) against the dense scan
+    and the oracle: tallies and TP flags identical, for the reference call and for the opt-in NMS variants."""
+    o, t = synth.make_batch(8, 231, "D2", 12)
+    o = synth.plant_detections(o, t, priors_cpu, 231, per_gt=4, jitter=0.3)
+    td = t.to(DEV)
+    for kw in ({}, {"iou_thresh": 0.45, "per_class": True, "score_thresh": 0.01, "top_k": 200}, {"top_k": 5}):
+        x = o.to(DEV)
+        res = ops.postprocess_(x, priors_gpu, want_lists=True, **kw)
+        dense, dflags = evaluate.accumulate(x, td, want_flags=True)
+        kept, kflags = evaluate.accumulate(x, td, want_flags=True, keep=res.keep, keep_cnt=res.keep_cnt)
+        assert torch.equal(dense, kept) and torch.equal(dflags, kflags)
+        want, _ = head.eval_batch(x.cpu(), t)
+        assert torch.equal(kept.cpu(), want)
+        assert int(kept[:, 0].sum()) > 0
+    # dense random-init image (thousands of kept rows) and an image with nothing kept
+    o1 = synth.make_outputs(2, 232, "D1")
+    o1[1, :, 4] += 30.0                                              # every row is void: no candidates
+    x = o1.to(DEV)
+    res = ops.postprocess_(x, priors_gpu, want_lists=True)
+    t1 = synth.make_targets(2, 232).to(DEV)
+    dense, _ = evaluate.accumulate(x, t1)
+    kept, _ = evaluate.accumulate(x, t1, keep=res.keep, keep_cnt=res.keep_cnt)
+    assert torch.equal(dense, kept) and int(res.keep_cnt[1]) == 0 and int(kept[:, 1].sum()) == int(res.keep_cnt[0])
+    with pytest.raises(ValueError):
+        evaluate.accumulate(x, t1, keep=res.keep)                    # keep without keep_cnt
+
+
+@pytest.mark.gpu
+def test_eval_overflow_is_reported():
+    """More than P positive score entries in one image (rows with several positive classes: input that skipped calc_score)
+    cannot be tallied by the dense scan; the status word is read back and raised instead of returning wrong tallies."""
+    from object_detection_torch2_b200 import _lib
+    x = torch.rand(1, 64, 25, device=DEV) + 0.1                      # 64 rows x 20 positive classes > P = 64
+    t = synth.make_targets(1, 7, 3).to(DEV)
+    with pytest.raises(_lib.SsdHeadError, match="more than P"):
+        evaluate.accumulate(x, t)
+    ok = torch.zeros(1, 64, 25, device=DEV)
+    ok[0, :, 6] = 0.5
+    evaluate.accumulate(ok, t)                                        # the status word was reset: the next call is clean
