@@ -389,8 +389,15 @@ def main():
         sampler.stop()
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Orderly exit without ncclCommDestroy: tearing a communicator down while CUDA graphs that captured its collectives are
+        # still alive has been seen to hang (N = 2, this image); the work is done and synchronised, so leave through _exit.
+        del graph
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -483,7 +490,7 @@ def bench_isolated(ctx, outs, tgts, grads):
     loss = torch.zeros(K, dtype=torch.float32, device=dev)
 
     def flush_l2():
-        torch.sum(flush, out=sink)
+        torch.sum(flush, dim=0, out=sink)
 
     def body_a():
         for k in range(K):

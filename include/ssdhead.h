@@ -121,6 +121,29 @@ SSDH_API int ssdh_multibox_loss_pipelined(const float* outputs, const float* tar
                        float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
                        void* ws, size_t ws_bytes, ssdh_stream_t stream, const float* next_outputs, const float* next_targets);
 
+/* Extended form: everything above plus the opt-in behaviours, selected through a versioned options record (NULL = the
+ * reference behaviour of ssdh_multibox_loss).
+ *   force_best_prior  north_star's "best-prior-per-GT forcing" (the reference has none, src/model/ssd.py:231-250):
+ *                     every real ground-truth box additionally claims its arg-max-IoU prior (lowest index on ties) when that
+ *                     IoU is positive.  0 = the reference.
+ *   inputs_stable     the contract of ssdh_multibox_loss_pipelined.
+ *   exact_math        libdevice exp / log and IEEE division instead of the approximate units (slower; for parity studies).
+ *   ce_override       test hook (needs exact_math): [N, P] cross-entropies the hard-negative selection is run on -- positive CE
+ *                     for matched priors, negative CE for the others -- so the selection logic can be checked on the checker's
+ *                     own numbers. */
+typedef struct ssdh_loss_options {
+  uint32_t struct_bytes;       /* = sizeof(ssdh_loss_options) */
+  int32_t force_best_prior;
+  int32_t inputs_stable;
+  int32_t exact_math;
+  const float* next_outputs;   /* as in ssdh_multibox_loss_pipelined, may be NULL */
+  const float* next_targets;
+  const float* ce_override;    /* may be NULL */
+} ssdh_loss_options;
+SSDH_API int ssdh_multibox_loss_ex(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
+                       float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
+                       void* ws, size_t ws_bytes, ssdh_stream_t stream, const ssdh_loss_options* options);
+
 /* Software pipelining hook: pull [ptr, ptr + bytes) from HBM into the L2 (cp.async.bulk.prefetch.L2), e.g. the NEXT
  * micro-batch's head output on a side stream while ssdh_multibox_loss works on the current one.  Reads nothing into
  * the SMs, changes no data; ptr must be 16-byte aligned. */

@@ -19,6 +19,12 @@ class ImageStats(ctypes.Structure):
                 ("k_pos", c_int32), ("k_neg", c_int32), ("pos_sel", c_int32), ("neg_sel", c_int32)]
 
 
+class LossOptions(ctypes.Structure):
+    """Mirror of ``ssdh_loss_options`` (include/ssdhead.h)."""
+    _fields_ = [("struct_bytes", ctypes.c_uint32), ("force_best_prior", c_int32), ("inputs_stable", c_int32), ("exact_math", c_int32),
+                ("next_outputs", c_void_p), ("next_targets", c_void_p), ("ce_override", c_void_p)]
+
+
 # name -> (restype, argtypes); the single source the symbol test checks against the header
 SIGNATURES = {
     "ssdh_version": (c_int, []),
@@ -37,6 +43,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssdh_multibox_loss_pipelined": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "ssdh_multibox_loss_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, POINTER(LossOptions)]),
     "ssdh_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "ssdh_prefetch_l2": (c_int, [c_void_p, c_size_t, c_void_p]),
     "ssdh_expand_targets": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

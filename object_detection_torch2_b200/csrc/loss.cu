@@ -1,1038 +1,11 @@
-// Fused MultiBox loss, forward + gradient in ONE launch.  Replaces SSD.loss and everything it calls
-// (reference src/model/ssd.py:181-328: _match, _calc_delta, _smooth_l1, _softmax_cross_entropy,
-// _split_pos_neg, _k_plus_1_th_value) plus the autograd backward of that graph (src/train.py:121).
-//
-// Decomposition (B200, sm_100a):
-//   * one thread-block CLUSTER per image (4 CTAs x 768 threads, one CTA per SM; 8 x 384 for bigger slabs).
-//     The image's contiguous [P, 4+C] slab is cut into 32-row blocks dealt round-robin to the CTAs, so every
-//     CTA sees the same mix of prior levels (equal matching work) and keeps its rows in shared memory for
-//     the whole kernel: HBM sees each output row exactly once as a read and (with grad) once as a write;
-//   * a warp's 32 lanes own one block per row slot: its blocks arrive by TMA bulk copies (cp.async.bulk) on the
-//     warp's own mbarriers, issued right after the (tiny, latency-critical) ground-truth rows landed; the IoU
-//     matching runs under the bulk load; nothing in the row phases needs a block-wide barrier;
-//   * one thread per row: log-sum-exp, positive / negative cross-entropy, smooth-L1 of matched pairs;
-//   * hard-negative mining = value threshold at the (k+1)-th largest CE (strict '>', ssd.py:222-223):
-//     a 256-bucket histogram (1/16-octave buckets of the CE) is combined through distributed shared memory,
-//     the bucket's candidates are gathered into every CTA and the exact order statistic is finished locally;
-//     only ONE of the two thresholds ever needs a search (see the split logic below);
-//   * gradient rows are written in place over the slab and leave by TMA bulk stores;
-//   * the last image to finish reduces the per-image losses in a fixed order (deterministic).
-#include <cooperative_groups.h>
-#include <stdlib.h>
-
-#include "common.cuh"
-
-namespace cg = cooperative_groups;
+// Fused MultiBox loss: C ABI entry points and the production / instrumented instantiations of multibox_loss_kernel
+// (loss_kernel.cuh).  Replaces SSD.loss and everything it calls (reference src/model/ssd.py:181-328) plus the autograd
+// backward of that graph (src/train.py:121).
+#include "loss_kernel.cuh"
 
 namespace ssdh {
-
-constexpr int kSlots = 3;            // rows per thread
-constexpr int kBlockRows = 32;       // rows per row slot of a warp
-constexpr int kChunkRows = kSlots * kBlockRows;   // rows dealt to one warp: 96 contiguous rows = one TMA copy in, three out
-constexpr int kMaxCluster = 8;
-constexpr int kMaxLossWarps = 32;
-constexpr int kListCap = 384;        // per-CTA candidates of the selected bucket
-constexpr int kGatherCap = 768;      // cluster-wide candidates finished locally
-// Two shapes of the same kernel (template parameters kT = threads per CTA, kCl = CTAs per cluster):
-//   <768, 4>: 4 CTAs x ~221 KB per image, one CTA per SM  -> every SM carries the same load (default when it fits)
-//   <384, 8>: 8 CTAs x ~110 KB per image                   -> larger images / more ground truth per image
-
-// Workspace record of one image.  The layout is independent of N so that the ticket words of a cached workspace are
-// always found zero again (they are reset by their last user), whatever batch size the previous call had.
-struct ImageSlot {          // 112 bytes
-  double part_loss[kMaxCluster];   // per-CTA partial sums
-  double image_loss;               // inv_pos * sum, ssd.py:227 before .mean()
-  int part_sel[kMaxCluster];       // selected positives | selected negatives << 16
-  unsigned int ticket;             // CTAs of this image that have delivered their partial
-  unsigned int pad;
-};
-
-struct LossParams {
-  const float* outputs;
-  const float* targets;
-  const float4* priors;
-  const float* next_outputs;   // optional: the next micro-batch (same shape), prefetched into L2 once this one is on chip
-  const float* next_targets;
-  int N, P, C, G;
-  float a;
-  ThrBand band;
-  float inv_n_global;
-  float* loss;
-  float* grad;
-  ssdh_image_stats* stats;
-  unsigned int* ticket;   // workspace: zero before first use, left zero
-  ImageSlot* slots;       // workspace [N]: per-CTA partial sums of one image + its arrival ticket (left zero)
-  int rows_per_cta;       // shared-memory rows reserved per CTA (multiple of kChunkRows)
-  int n_chunks;           // ceil(P / kChunkRows)
-  int bulk;               // 1: every block is 16-byte aligned/sized -> TMA path
-  int early_inputs;       // 1: outputs / targets / priors were complete before the PREVIOUS kernel of the stream started, so they
-                          //    may be read under that kernel's tail (programmatic dependent launch); 0: wait for it first
-  unsigned long long* trace;   // debug: [grid][kTracePoints] SM clock stamps (NULL in production)
-};
-
-constexpr int kTracePoints = 64;
-template <bool kTrace>
-__device__ __forceinline__ void trace_point_t(const LossParams& p, int idx) {
-  if (kTrace && p.trace != nullptr && threadIdx.x == 0) {
-    unsigned long long t;
-    if (idx == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    else t = clock64();
-    p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + idx] = t;
-  }
-}
-
-struct GtRec {             // 48 bytes, one per ground-truth row of the image; three 16-byte groups = three loads
-  float x1, x2, y1, y2;    // corners                      (ssd.py:247-248)       -- matching
-  float cx, cy, lw, lh;    // lw = log(w) (or w when w <= 0, ssd.py:269)           -- offsets of a matched pair
-  float area;              //                                                     -- matching
-  float tsum;              // sum of the class vector
-  int label;               // class index when the class vector is exactly one-hot, else -1   -- matched pair (with flags)
-  int flags;               // bit0: w > 0, bit1: h > 0
-};
-
-struct LossShared {
-  uint32_t hist[2][2][128];   // [buffer][set][256 bins packed as 2 x u16]
-  uint32_t tot[2][128];       // cluster-wide packed totals
-  uint32_t list[kListCap];    // my candidates of the selected bucket (read remotely)
-  uint32_t gathered[kGatherCap];
-  unsigned long long mbar[kSlots][kMaxLossWarps];   // one per (row slot, warp): a warp's 32 rows are one dealt block
-  uint8_t gt_fast[kMaxGT], gt_slow[kMaxGT];          // ground-truth rows by matching path (see the match section)
-  int n_fast, n_slow, soft_labels;
-  double wred_loss[kMaxLossWarps];
-  int wred_a[kMaxLossWarps], wred_b[kMaxLossWarps];
-  int pos_local, list_cnt;                // read remotely
-  int pos_raw, k_pos, k_neg, sel_set, need_select, overflow, n_gathered;
-  uint32_t sel_prefix, sel_rem;
-};
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// Same, with an L2 eviction policy: the head output is read exactly once, so its lines should be the first victims
-// (keeps the freshly written gradient -- which the backbone's backward reads next -- resident instead).
-__device__ __forceinline__ unsigned long long policy_evict_first() {
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar, unsigned long long pol) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// Cluster barrier for data that lives in the WRITER's own shared memory (histograms, candidate lists, counters) and is
-// read by the peers through distributed shared memory afterwards.  cooperative groups' cluster.sync() arrives with
-// .release at cluster scope, which this chip implements as MEMBAR.ALL.GPU (+ ERRBAR / CGAERRBAR): it drains every
-// outstanding memory operation of the SM, ~0.5 k cycles with TMA traffic in flight.  For writes to one's own shared
-// memory a CTA-scope fence is enough -- once MEMBAR.ALL.CTA has retired they ARE in the SM's shared memory, which is
-// where a peer's remote load looks (the same reliance CUTLASS places on mbarrier.init + cluster_arrive_relaxed).
-__device__ __forceinline__ void cluster_arrive_own_smem() {
-  __syncwarp();
-  asm volatile("fence.acq_rel.cta;" ::: "memory");
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void cluster_arrive_nodata() { __syncwarp(); asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_acquire() { __syncwarp(); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Packed fp32 pairs (FFMA2 / FADD2 on sm_100a): one issue slot for two lanes of the class loop.
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-__device__ __forceinline__ float smooth_l1_f(float x) {
-  const float ax = fabsf(x);
-  return ax < 1.0f ? 0.5f * x * x : ax - 0.5f;
-}
-__device__ __forceinline__ float clamp1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
-
-// In place: x[c] <- scale * exp(x[c] - lse), the softmax gradient term of one row of logits in shared memory.
-template <int kC>
-__device__ __forceinline__ void softmax_scaled(float* x, int C, float lse, float scale) {
-  constexpr float kLog2e = 1.4426950408889634f;
-  const float nls = -(lse * kLog2e);
-  if (kC > 0) {
-    const unsigned long long l2 = pack2(kLog2e, kLog2e), m2 = pack2(nls, nls), sc2 = pack2(scale, scale);
-#pragma unroll
-    for (int c = 0; c + 1 < kC; c += 2) {
-      float a0, a1;
-      unpack2(ffma2(pack2(x[c], x[c + 1]), l2, m2), a0, a1);
-      unpack2(fmul2(pack2(ex2_approx(a0), ex2_approx(a1)), sc2), a0, a1);
-      x[c] = a0;
-      x[c + 1] = a1;
-    }
-    if (kC & 1) x[kC - 1] = scale * ex2_approx(fmaf(x[kC - 1], kLog2e, nls));
-  } else {
-    for (int c = 0; c < C; ++c) x[c] = scale * ex2_approx(fmaf(x[c], kLog2e, nls));
-  }
-}
-
-// Monotone (non-decreasing in the order key) 8-bit bucket: 16 buckets per octave over [2^-12, 2^4), everything
-// below / above clamps into the first / last bucket.  Cross-entropies of interest live well inside the window.
-__device__ __forceinline__ uint32_t bucket_of(uint32_t key) {
-  const int v = static_cast<int>(key >> 19) - (4096 + ((127 - 12) << 4));
-  return static_cast<uint32_t>(min(max(v, 0), 255));
-}
-
-// One warp: find the bin holding the (rem+1)-th largest element of a 256-bin packed histogram.
-// Returns bin in [0,255]; rem is updated to the rank inside that bin.  All lanes get the result.
-__device__ __forceinline__ int find_bin_desc(const uint32_t* packed, uint32_t& rem, int lane) {
-  // lane l owns bins [248 - 8l, 255 - 8l], i.e. packed words [124 - 4l, 127 - 4l]
-  const uint4 w = *reinterpret_cast<const uint4*>(packed + 124 - 4 * lane);
-  uint32_t c[8];   // c[0] = highest bin of the lane
-  c[0] = w.w >> 16; c[1] = w.w & 0xffffu; c[2] = w.z >> 16; c[3] = w.z & 0xffffu;
-  c[4] = w.y >> 16; c[5] = w.y & 0xffffu; c[6] = w.x >> 16; c[7] = w.x & 0xffffu;
-  int s = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s += static_cast<int>(c[i]);
-  const int incl = warp_incl_scan(s, lane);
-  const uint32_t ballot = __ballot_sync(0xffffffffu, static_cast<uint32_t>(incl) > rem);
-  const int owner = ballot ? (__ffs(ballot) - 1) : 31;
-  // inside the owner's 8 bins (descending): first i with rem' < c[0] + ... + c[i], branch-free
-  const uint32_t r0 = rem - static_cast<uint32_t>(incl - s);
-  uint32_t cum = 0, below = 0;
-  int idx = 0;
-#pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    cum += c[i];
-    const bool past = r0 >= cum;
-    idx += past ? 1 : 0;
-    below = past ? cum : below;
-  }
-  int bin = 255 - 8 * lane - idx;
-  uint32_t r = r0 - below;
-  bin = __shfl_sync(0xffffffffu, bin, owner);
-  rem = __shfl_sync(0xffffffffu, r, owner);
-  return bin;
-}
-
-// Warp-aggregated histogram add: lanes with the same (set, bin) elect one lane to add their count.
-__device__ __forceinline__ void hist_add(uint32_t* hist_set0, bool active, int set, uint32_t bin, int lane) {
-  const uint32_t tag = active ? (static_cast<uint32_t>(set) << 8 | bin) : 0xffffffffu;
-  const uint32_t peers = __match_any_sync(0xffffffffu, tag);
-  if (active && lane == __ffs(peers) - 1)
-    atomicAdd(hist_set0 + set * 128 + (bin >> 1), static_cast<uint32_t>(__popc(peers)) << (16 * (bin & 1u)));
-}
-
-template <int kC, int kLossThreads, int kCluster, bool kTrace>
-__global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const LossParams p) {
-  constexpr int kLossWarps = kLossThreads / 32;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = static_cast<int>(cluster.block_rank());
-  const int n = blockIdx.x / kCluster;
-  const int C = kC ? kC : p.C;
-  const int row = 4 + C;
-  const int G = p.G;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  // The image is cut into 96-row chunks dealt round-robin to the CTAs of the cluster (every CTA sees the same mix of
-  // prior levels); inside a CTA, warp w owns local chunk w: global chunk w * kCluster + rank, rows [32 s, 32 s + 32) of
-  // it are the warp's row slot s.  One TMA copy brings the chunk in, one per slot takes the gradient out.
-  const int my_chunks = (p.n_chunks - rank + kCluster - 1) / kCluster;
-  const int my_chunk = warp * kCluster + rank;                                   // global chunk of this warp
-  const int my_rows_w = warp < my_chunks ? min(kChunkRows, p.P - my_chunk * kChunkRows) : 0;   // rows this warp owns
-  constexpr float kLog2e = 1.4426950408889634f;
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* slab = reinterpret_cast<float*>(smem_raw);
-  const size_t slab_bytes = (static_cast<size_t>(p.rows_per_cta) * row * sizeof(float) + 15) & ~static_cast<size_t>(15);
-  GtRec* gts = reinterpret_cast<GtRec*>(smem_raw + slab_bytes);
-  LossShared& sh = *reinterpret_cast<LossShared*>(smem_raw + slab_bytes + ((static_cast<size_t>(G) * sizeof(GtRec) + 15) & ~static_cast<size_t>(15)));
-
-  const float* img_in = p.outputs + static_cast<size_t>(n) * p.P * row;
-
-  // Programmatic dependent launch: let the NEXT grid in the stream be scheduled as soon as SMs free up.  It may run
-  // everything that only reads its own inputs (load, match, CE, selection) under this grid's tail; it blocks at
-  // griddepcontrol.wait below, before its first global write (workspace, loss, stats, gradient).
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  // The kernel in front of us in the stream is normally the PRODUCER of outputs / targets (the head's last kernel, a copy,
-  // ssdh_expand_targets ...): its writes are only guaranteed visible after griddepcontrol.wait, so unless the caller vouches
-  // for the inputs (ssdh_multibox_loss_pipelined) nothing is read from global memory before this point.
-  if (!p.early_inputs) asm volatile("griddepcontrol.wait;" ::: "memory");
-
-  // ---- setup ------------------------------------------------------------------------------------
-  trace_point_t<kTrace>(p, 0);
-  trace_point_t<kTrace>(p, 1);
-  float4 pri[kSlots];
-  bool valid[kSlots];
-#pragma unroll
-  for (int s = 0; s < kSlots; ++s) {
-    const int grow = my_chunk * kChunkRows + s * kBlockRows + lane;
-    valid[s] = s * kBlockRows + lane < my_rows_w;
-    pri[s] = __ldg(p.priors + (valid[s] ? grow : 0));
-  }
-  if (tid == 0) {
-    sh.pos_local = 0;
-    sh.list_cnt = 0;
-    sh.n_fast = 0;
-    sh.n_slow = 0;
-    sh.soft_labels = 0;
-  }
-  for (int i = tid; i < 2 * 2 * 128; i += kLossThreads) (&sh.hist[0][0][0])[i] = 0u;
-  __syncthreads();
-
-  // The (tiny) ground-truth rows are requested first so they are not queued behind the slab traffic.
-  float gt_first = 0.0f;
-  if (warp < G) gt_first = __ldg(p.targets + (static_cast<size_t>(n) * G + warp) * row + min(lane, row - 1));
-
-  // ---- slab: every warp fetches its own 96-row chunk with ONE TMA bulk copy onto its own mbarrier; issued right
-  // behind the (tiny) ground-truth request, so that it lands while the ground truth is being unpacked -----------------
-  float* my_slab = slab + static_cast<size_t>(warp) * kChunkRows * row;
-  if (p.bulk) {
-    if (lane == 0) {
-      mbar_init(&sh.mbar[0][warp], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      if (my_rows_w > 0) {
-        const uint32_t bytes = static_cast<uint32_t>(my_rows_w) * row * sizeof(float);
-        mbar_expect_tx(&sh.mbar[0][warp], bytes);
-        bulk_load_hint(my_slab, img_in + static_cast<size_t>(my_chunk) * kChunkRows * row, bytes, &sh.mbar[0][warp], policy_evict_first());
-      }
-    }
-    __syncwarp();
-  } else {
-    const float* src = img_in + static_cast<size_t>(my_chunk) * kChunkRows * row;
-#pragma unroll 1
-    for (int i = lane; i < my_rows_w * row; i += 32) my_slab[i] = src[i];
-    __syncwarp();
-  }
-
-  // ---- ground truth of this image -> shared: one warp per row, one coalesced request each -----------------
-  for (int g = warp; g < G; g += kLossWarps) {
-    const float* tr = p.targets + (static_cast<size_t>(n) * G + g) * row;
-    float box = 0.0f, tsum = 0.0f;
-    int nz = 0, ones = 0, label = -1;
-    for (int base = 0; base < row; base += 32) {
-      const int c = base + lane;
-      const float v = (base == 0 && g == warp) ? (c < row ? gt_first : 0.0f) : (c < row ? __ldg(tr + c) : 0.0f);
-      if (base == 0) box = v;
-      const bool cls = c >= 4 && c < row;
-      const uint32_t b_nz = __ballot_sync(0xffffffffu, cls && v != 0.0f);
-      const uint32_t b_one = __ballot_sync(0xffffffffu, cls && v == 1.0f);
-      nz += __popc(b_nz);
-      ones += __popc(b_one);
-      if (b_one) label = base + __ffs(b_one) - 1 - 4;
-      tsum += warp_sum(cls ? v : 0.0f);
-    }
-    const float gcx = __shfl_sync(0xffffffffu, box, 0), gcy = __shfl_sync(0xffffffffu, box, 1);
-    const float gw = __shfl_sync(0xffffffffu, box, 2), gh = __shfl_sync(0xffffffffu, box, 3);
-    if (lane == 0) {
-      const Corners c = make_corners(gcx, gcy, gw, gh);
-      GtRec r;
-      r.x1 = c.x1; r.x2 = c.x2; r.y1 = c.y1; r.y2 = c.y2;
-      r.area = c.area; r.cx = gcx; r.cy = gcy;
-      r.lw = gw > 0.0f ? logf(gw) : gw;
-      r.lh = gh > 0.0f ? logf(gh) : gh;
-      r.flags = (gw > 0.0f ? 1 : 0) | (gh > 0.0f ? 2 : 0);
-      r.label = (nz == 1 && ones == 1) ? label : -1;
-      r.tsum = tsum;
-      gts[g] = r;
-      // fast path: a normal positive area lets the band test decide IoU > thr without dividing; everything else
-      // (padding rows, degenerate or denormal boxes, exotic thresholds) takes the exact path
-      if (p.band.usable && c.area >= 1e-30f && c.area <= 1e30f) sh.gt_fast[atomicAdd(&sh.n_fast, 1)] = static_cast<uint8_t>(g);
-      else if (c.area > 0.0f || c.area > p.band.thr || !(c.area == c.area)) sh.gt_slow[atomicAdd(&sh.n_slow, 1)] = static_cast<uint8_t>(g);
-      if (r.label < 0 && c.area > 0.0f) sh.soft_labels = 1;
-    }
-  }
-    // ---- corners of my priors and the outer bounds of my whole chunk (box around its priors, smallest / largest prior
-  // area), used below to drop ground-truth rows that cannot match ANY of them ------------------------------------
-  Corners d[kSlots];
-  float cb_x1 = 3e38f, cb_x2 = -3e38f, cb_y1 = 3e38f, cb_y2 = -3e38f, cb_amin = 3e38f, cb_amax = -3e38f;
-  bool tame = true;                        // every prior of the chunk has finite positive width and height
-#pragma unroll
-  for (int s = 0; s < kSlots; ++s) {
-    d[s] = make_corners(pri[s].x, pri[s].y, pri[s].z, pri[s].w);
-    if (valid[s]) {
-      cb_x1 = fminf(cb_x1, d[s].x1); cb_x2 = fmaxf(cb_x2, d[s].x2);
-      cb_y1 = fminf(cb_y1, d[s].y1); cb_y2 = fmaxf(cb_y2, d[s].y2);
-      cb_amin = fminf(cb_amin, d[s].area); cb_amax = fmaxf(cb_amax, d[s].area);
-      tame = tame && pri[s].z > 0.0f && pri[s].w > 0.0f && pri[s].z < 1e18f && pri[s].w < 1e18f && fabsf(pri[s].x) < 1e18f && fabsf(pri[s].y) < 1e18f;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    cb_x1 = fminf(cb_x1, __shfl_xor_sync(0xffffffffu, cb_x1, o)); cb_x2 = fmaxf(cb_x2, __shfl_xor_sync(0xffffffffu, cb_x2, o));
-    cb_y1 = fminf(cb_y1, __shfl_xor_sync(0xffffffffu, cb_y1, o)); cb_y2 = fmaxf(cb_y2, __shfl_xor_sync(0xffffffffu, cb_y2, o));
-    cb_amin = fminf(cb_amin, __shfl_xor_sync(0xffffffffu, cb_amin, o)); cb_amax = fmaxf(cb_amax, __shfl_xor_sync(0xffffffffu, cb_amax, o));
-  }
-  tame = __all_sync(0xffffffffu, tame);
-
-  __syncthreads();
-
-  trace_point_t<kTrace>(p, 2);
-  // ---- matching: bit g of (mhi:mlo)[s] = IoU(gt g, prior) > thr   (ssd.py:231-250) ----------------------------
-  // Dense pass over the fast rows, branch-free and division-free.  e = inter - union * thr is one FMA, so its sign
-  // is exact; |e| > union * thr * 2^-20 then decides fl(inter / union) > thr with certainty either way.  The
-  // (one in millions) pairs inside that band flag the thread through `amb`, and a flagged thread redoes its pairs
-  // with the IEEE division, so the final mask is bit-identical to torch's.  The min / max / compare / logic ops
-  // issue at half rate on this SM, hence the care to keep them at 9 per pair.
-  uint32_t mlo[kSlots], mhi[kSlots];
-#pragma unroll
-  for (int s = 0; s < kSlots; ++s) { mlo[s] = 0u; mhi[s] = 0u; }
-  {
-    const ThrBand band = p.band;
-    const float nthr = -band.thr, eps = band.thr * 9.5367431640625e-07f;
-    const int n_fast = sh.n_fast, n_slow = sh.n_slow;
-    // Cull: lane i looks at fast row i (and i + 32).  IoU > thr needs inter * (1 + thr) > thr * (area_g + area_p), and
-    // inter can exceed neither the overlap of the row with the chunk's outer box nor either area; a row that fails this
-    // bound (with a 1e-4 safety margin, far above any rounding) for the chunk's extreme areas matches none of my priors.
-    uint32_t keep_lo = 0u, keep_hi = 0u;
-    {
-      const float thr = band.thr;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (half == 1 && n_fast <= 32) break;            // uniform
-        const int i = 32 * half + lane;
-        const bool have = i < n_fast;
-        const int g = have ? sh.gt_fast[i] : 0;
-        const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
-        const float garea = gts[g].area;
-        const float w = fmaxf(fminf(q.y, cb_x2) - fmaxf(q.x, cb_x1), 0.0f);
-        const float h = fmaxf(fminf(q.w, cb_y2) - fmaxf(q.z, cb_y1), 0.0f);
-        const float imax = fminf(fminf(w * h, cb_amax), garea);
-        const bool hopeless = imax * (1.0f + thr) <= thr * (garea + cb_amin) * 0.9999f;
-        const uint32_t k = __ballot_sync(0xffffffffu, have && !(tame && hopeless));
-        if (half == 0) keep_lo = k; else keep_hi = k;
-      }
-    }
-    float amb = 1.0f;                              // min over pairs of |e| - margin; <= 0 means "settle exactly"
-    const int n_keep = __popc(keep_lo) + __popc(keep_hi);
-#pragma unroll 2
-    for (int it = 0; it < n_keep; ++it) {
-      int i;
-      if (keep_lo) { i = __ffs(keep_lo) - 1; keep_lo &= keep_lo - 1; }
-      else { i = 32 + __ffs(keep_hi) - 1; keep_hi &= keep_hi - 1; }
-      const int g = sh.gt_fast[i];
-      const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
-      const float garea = gts[g].area;
-      const uint32_t bit = 1u << (g & 31);
-      if (g < 32) {
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-          const float w = fmaxf(fminf(q.y, d[s].x2) - fmaxf(q.x, d[s].x1), 0.0f);
-          const float h = fmaxf(fminf(q.w, d[s].y2) - fmaxf(q.z, d[s].y1), 0.0f);
-          const float inter = w * h;
-          const float uni = (garea + d[s].area) - inter;
-          const float e = fmaf(uni, nthr, inter), m = uni * eps;
-          amb = fminf(amb, fabsf(e) - m);
-          if (e > m) mlo[s] |= bit;
-        }
-      } else {
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-          const float w = fmaxf(fminf(q.y, d[s].x2) - fmaxf(q.x, d[s].x1), 0.0f);
-          const float h = fmaxf(fminf(q.w, d[s].y2) - fmaxf(q.z, d[s].y1), 0.0f);
-          const float inter = w * h;
-          const float uni = (garea + d[s].area) - inter;
-          const float e = fmaf(uni, nthr, inter), m = uni * eps;
-          amb = fminf(amb, fabsf(e) - m);
-          if (e > m) mhi[s] |= bit;
-        }
-      }
-    }
-    // the band argument needs a positive union: chunks holding a prior of non-positive or non-finite extent settle exactly
-    const bool unsure = !(amb > 0.0f) || !tame;
-    if (__any_sync(0xffffffffu, unsure) || n_slow > 0) {
-      const int n_exact = n_slow + (unsure ? n_fast : 0);
-      for (int i = 0; i < n_exact; ++i) {          // exact path: borderline pairs, exotic rows / thresholds
-        const int g = i < n_slow ? sh.gt_slow[i] : sh.gt_fast[i - n_slow];
-        const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
-        const float garea = gts[g].area;
-        const uint32_t bit = 1u << (g & 31);
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-          const float w = fmaxf(fminf(q.y, d[s].x2) - fmaxf(q.x, d[s].x1), 0.0f);
-          const float h = fmaxf(fminf(q.w, d[s].y2) - fmaxf(q.z, d[s].y1), 0.0f);
-          const float inter = w * h;
-          const float val = garea > 0.0f ? __fdiv_rn(inter, (garea + d[s].area) - inter) : garea;     // ssd.py:250
-          const bool hit = val > band.thr;
-          if (g < 32) mlo[s] = hit ? (mlo[s] | bit) : (mlo[s] & ~bit);
-          else mhi[s] = hit ? (mhi[s] | bit) : (mhi[s] & ~bit);
-        }
-      }
-    }
-  }
-  trace_point_t<kTrace>(p, 3);
-
-  // ---- per-row terms ----------------------------------------------------------------------------------
-  // ce: positive CE (matched rows) or negative CE (unmatched rows); lloc: smooth-L1 sum; lse: log-sum-exp.
-  // Matched rows leave sum_g clamp(l - g_hat, -1, 1) -- the localisation gradient -- in their offset columns.
-  float ce[kSlots], lloc[kSlots], lse[kSlots];
-#pragma unroll
-  for (int s = 0; s < kSlots; ++s) {
-    ce[s] = 0.0f; lloc[s] = 0.0f; lse[s] = 0.0f;
-    if (s * kBlockRows >= my_rows_w) continue;                      // uniform per warp
-    if (p.bulk && s == 0) mbar_wait(&sh.mbar[0][warp], 0);          // the whole chunk lands on one barrier
-    if (s == 0) trace_point_t<kTrace>(p, 4);
-    float* rp = my_slab + static_cast<size_t>(s * kBlockRows + lane) * row;
-    if (valid[s]) {
-      float mx, sum = 0.0f;
-      if (kC > 0) {
-        float x[kC > 0 ? kC : 1];
-#pragma unroll
-        for (int c = 0; c < kC; ++c) x[c] = rp[4 + c];
-        mx = x[0];
-#pragma unroll
-        for (int c = 1; c + 1 < kC; c += 2) mx = fmaxf(mx, fmaxf(x[c], x[c + 1]));       // FMNMX3
-        if ((kC & 1) == 0) mx = fmaxf(mx, x[kC - 1]);
-        const float nmxs = -(mx * kLog2e);
-        const unsigned long long l2 = pack2(kLog2e, kLog2e), m2 = pack2(nmxs, nmxs);
-        unsigned long long acc2 = pack2(0.0f, 0.0f);
-#pragma unroll
-        for (int c = 0; c + 1 < kC; c += 2) {                                             // FFMA2 / FADD2: two classes per slot
-          float a0, a1;
-          unpack2(ffma2(pack2(x[c], x[c + 1]), l2, m2), a0, a1);
-          acc2 = fadd2(acc2, pack2(ex2_approx(a0), ex2_approx(a1)));
-        }
-        float s0, s1;
-        unpack2(acc2, s0, s1);
-        sum = s0 + s1;
-        if (kC & 1) sum += ex2_approx(fmaf(x[kC - 1], kLog2e, nmxs));
-      } else {
-        mx = rp[4];
-        for (int c = 1; c < C; ++c) mx = fmaxf(mx, rp[4 + c]);
-        const float mxs = mx * kLog2e;
-        for (int c = 0; c < C; ++c) sum += ex2_approx(fmaf(rp[4 + c], kLog2e, -mxs));
-      }
-      const float ls = __logf(sum);                                  // lg2.approx: |error| ~1e-7 on sums in [1, C], ample for 1e-5
-      lse[s] = mx + ls;
-      ce[s] = ls - (rp[4] - mx);                                     // -log_softmax[void]   (ssd.py:212-215)
-      if ((mlo[s] | mhi[s]) != 0u) {
-        const float4 q = pri[s];
-        const float ldw = __logf(q.z), ldh = __logf(q.w);             // offsets only feed loss values: fast math is ample
-        const float rdw = __fdividef(1.0f, q.z), rdh = __fdividef(1.0f, q.w);
-        const float l0 = rp[0], l1 = rp[1], l2 = rp[2], l3 = rp[3];
-        // l - g-hat per matched row (ssd.py:202-204, 267-270) = (l + d_c / d_w) - g_c / d_w and (l + log d_w) - log g_w:
-        // the prior-only parts are hoisted, leaving one FMA / one add per coordinate and pair
-        const float a0 = fmaf(q.x, rdw, l0), a1 = fmaf(q.y, rdh, l1), b2 = l2 + ldw, b3 = l3 + ldh;
-        float acc_ce = 0.0f, acc_loc = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t m = half ? mhi[s] : mlo[s];
-          while (m) {
-            const int g = 32 * half + __ffs(m) - 1;
-            m &= m - 1;
-            const float4 go = *reinterpret_cast<const float4*>(&gts[g].cx);      // cx, cy, lw, lh
-            const int2 lf = *reinterpret_cast<const int2*>(&gts[g].label);         // label, flags
-            if (lf.x >= 0) {
-              acc_ce += ls - (rp[4 + lf.x] - mx);                    // -log_softmax[label]  (ssd.py:208-209)
-            } else {
-              const float* tw = p.targets + (static_cast<size_t>(n) * G + g) * row + 4;
-              float dot = 0.0f;
-#pragma unroll 1
-              for (int c = 0; c < C; ++c) dot += tw[c] * ((rp[4 + c] - mx) - ls);      // soft labels: rare, kept small
-              acc_ce += -dot;
-            }
-            const float x0 = fmaf(-go.x, rdw, a0);
-            const float x1 = fmaf(-go.y, rdh, a1);
-            const float x2 = ((lf.y & 1) ? b2 : l2) - go.z;
-            const float x3 = ((lf.y & 2) ? b3 : l3) - go.w;
-            // with c = clamp(x, -1, 1): smooth_l1(x) = c * (x - c / 2)  (ssd.py:283) and c is its derivative
-            const float c0 = clamp1(x0), c1 = clamp1(x1), c2 = clamp1(x2), c3 = clamp1(x3);
-            acc_loc = fmaf(c0, fmaf(-0.5f, c0, x0), acc_loc);
-            acc_loc = fmaf(c1, fmaf(-0.5f, c1, x1), acc_loc);
-            acc_loc = fmaf(c2, fmaf(-0.5f, c2, x2), acc_loc);
-            acc_loc = fmaf(c3, fmaf(-0.5f, c3, x3), acc_loc);
-            g0 += c0; g1 += c1; g2 += c2; g3 += c3;
-          }
-        }
-        ce[s] = acc_ce;
-        lloc[s] = acc_loc;
-        rp[0] = g0; rp[1] = g1; rp[2] = g2; rp[3] = g3;
-      }
-    }
-    if (valid[s]) {
-      const uint32_t b = bucket_of(float_key(ce[s]));
-      atomicAdd(&sh.hist[0][(mlo[s] | mhi[s]) != 0u ? 0 : 1][b >> 1], 1u << (16 * (b & 1u)));
-    }
-  }
-
-  {
-    int c = 0;
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) c += (valid[s] && (mlo[s] | mhi[s]) != 0u) ? 1 : 0;
-    c = warp_sum(c);
-    if (lane == 0 && c) atomicAdd(&sh.pos_local, c);
-  }
-
-  if (kTrace && p.trace != nullptr && lane == 0) p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 24 + warp] = clock64();   // per-warp end of the row phase
-
-  // ---- software pipelining across micro-batches: HBM goes quiet from here until the gradient leaves, so every
-  // warp now asks the L2 for the same blocks of the NEXT batch (this SM will read them again in the next launch) ------
-  if (p.next_outputs != nullptr && p.bulk && lane == 0 && my_rows_w > 0) {
-    const uint32_t bytes = static_cast<uint32_t>(my_rows_w) * row * sizeof(float);
-    const float* nsrc = p.next_outputs + static_cast<size_t>(n) * p.P * row + static_cast<size_t>(my_chunk) * kChunkRows * row;
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc), "r"(bytes) : "memory");
-  }
-  if (p.next_targets != nullptr && rank == 0 && tid == 32 && G > 0) {
-    const uint32_t bytes = (static_cast<uint32_t>(G) * row * sizeof(float)) & ~15u;
-    const float* nt = p.next_targets + static_cast<size_t>(n) * G * row;
-    if (bytes && (reinterpret_cast<uintptr_t>(nt) & 15u) == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nt), "r"(bytes) : "memory");
-  }
-
-  // ---- cluster exchange #1: positives + bucket histograms of both sets -----------------------------------------
-  trace_point_t<kTrace>(p, 5);
-  cluster_arrive_own_smem();
-  cluster_wait_acquire();
-  trace_point_t<kTrace>(p, 6);
-  if (tid < 256) {
-    const int set = tid >> 7, w = tid & 127;
-    uint32_t t = 0;
-#pragma unroll
-    for (int r = 0; r < kCluster; ++r) t += *cluster.map_shared_rank(&sh.hist[0][set][w], r);
-    sh.tot[set][w] = t;
-  } else if (warp == 8) {
-    int v = (lane < kCluster) ? *cluster.map_shared_rank(&sh.pos_local, lane) : 0;
-    v = warp_sum(v);
-    if (lane == 0) sh.pos_raw = v;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    // 3:1 split (ssd.py:218-220, 310-311) and which threshold needs a search.  Rows outside a set
-    // contribute exact zeros to that set's CE array, so with M members and k <= M the (k+1)-th largest
-    // is 0 whenever k == M; k < M happens for at most one of the two sets.
-    const int pos_raw = sh.pos_raw, neg_raw = p.P - pos_raw;
-    const bool crowded = pos_raw * 3 > neg_raw;
-    const int k_pos = crowded ? neg_raw / 3 : pos_raw;
-    const int k_neg = crowded ? neg_raw : pos_raw * 3;
-    int set = -1, k = 0;
-    if (k_pos < pos_raw) { set = 0; k = k_pos; }
-    else if (k_neg < neg_raw) { set = 1; k = k_neg; }
-    uint32_t rem = static_cast<uint32_t>(k);
-    int bin = 0;
-    if (set >= 0) bin = find_bin_desc(sh.tot[set], rem, lane);
-    if (lane == 0) {
-      sh.k_pos = k_pos; sh.k_neg = k_neg;
-      sh.sel_set = set; sh.need_select = set >= 0;
-      sh.sel_prefix = static_cast<uint32_t>(bin);       // selected bucket
-      sh.sel_rem = rem;                                 // rank of the answer inside the bucket
-    }
-  }
-  __syncthreads();
-  // The local radix passes reuse hist[1][*] (never touched outside the fallback) and tot[*] as their four zeroed
-  // histograms; tot is free from here on (the cluster barrier below orders this clear before its reuse).
-  if (tid < 256) (&sh.tot[0][0])[tid] = 0u;
-  trace_point_t<kTrace>(p, 7);
-
-  const int sel_set = sh.sel_set;
-  const bool need_select = sh.need_select != 0;
-  uint32_t sel_key = 0;          // order key of the searched threshold (identical in every thread of the cluster)
-  if (need_select) {
-    // my candidates of the selected bucket -> sh.list (order is irrelevant)
-    const uint32_t bucket = sh.sel_prefix;
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-      if (s * kBlockRows >= my_rows_w) continue;                    // uniform per warp
-      const uint32_t key = float_key(ce[s]);
-      const bool member = valid[s] && (((mlo[s] | mhi[s]) != 0u) == (sel_set == 0)) && (bucket_of(key) == bucket);
-      const uint32_t ballot = __ballot_sync(0xffffffffu, member);
-      int base = 0;
-      if (lane == 0 && ballot) base = atomicAdd(&sh.list_cnt, __popc(ballot));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      const int pos = base + __popc(ballot & lt_mask);
-      if (member && pos < kListCap) sh.list[pos] = key;
-    }
-    trace_point_t<kTrace>(p, 16);
-    cluster_arrive_own_smem();
-    cluster_wait_acquire();
-    trace_point_t<kTrace>(p, 17);
-    // everyone gathers every CTA's candidates and finishes the order statistic locally
-    int cnt[kCluster], total = 0;
-    bool over = false;
-#pragma unroll
-    for (int r = 0; r < kCluster; ++r) {
-      cnt[r] = *cluster.map_shared_rank(&sh.list_cnt, r);
-      over |= cnt[r] > kListCap;
-      total += cnt[r];
-    }
-    over |= total > kGatherCap;
-    uint32_t prefix = 0, rem = sh.sel_rem;
-    if (!over) {
-      for (int i = tid; i < total; i += kLossThreads) {
-        int r = 0, off = i;
-#pragma unroll
-        for (int q = 0; q < kCluster - 1; ++q)
-          if (r == q && off >= cnt[q]) { off -= cnt[q]; r = q + 1; }
-        sh.gathered[i] = cluster.map_shared_rank(&sh.list[0], r)[off];
-      }
-      __syncthreads();
-      trace_point_t<kTrace>(p, 18);
-      if (total <= 256) {
-        // few candidates (the usual case): exact order statistic by counting, spread over the whole CTA.  With
-        // above(v) = #{candidates > v}, the (rem+1)-th largest is the SMALLEST key whose above() is <= rem.  Thread t
-        // compares candidate t % 256 with one part of the list and adds its partial count (tot[] is zero here).
-        uint32_t* cnt_above = &sh.tot[0][0];
-        constexpr int kParts = kLossThreads / 256;                 // 3 with 768 threads, 1 with 384
-        const int ci = tid & 255, part = tid >> 8;
-        if (tid == 0) sh.sel_prefix = 0xffffffffu;
-        if (ci < total && part < kParts) {
-          const uint32_t mine = sh.gathered[ci];
-          const int per = (((total + kParts - 1) / kParts) + 3) & ~3;
-          const int j0 = part * per, j1 = min(total, j0 + per);
-          int above = 0;
-          int j = j0;
-          for (; j + 4 <= j1; j += 4) {
-            const uint4 v = *reinterpret_cast<const uint4*>(&sh.gathered[j]);
-            above += (v.x > mine) + (v.y > mine) + (v.z > mine) + (v.w > mine);
-          }
-          for (; j < j1; ++j) above += sh.gathered[j] > mine;
-          if (above) atomicAdd(&cnt_above[ci], static_cast<uint32_t>(above));
-        }
-        __syncthreads();
-        if (tid < total && cnt_above[tid] <= rem) atomicMin(&sh.sel_prefix, sh.gathered[tid]);
-        __syncthreads();
-        prefix = sh.sel_prefix;
-      } else {
-      // Interior buckets pin the top 13 bits of the key: 19 bits remain -> 3 passes (8 + 8 + 3); the two clamped
-      // end buckets span arbitrary keys -> 4 full passes.  One buffer per pass, one barrier per pass; every warp
-      // resolves the bin redundantly from the same histogram.
-      const bool interior = bucket > 0u && bucket < 255u;
-      const int n_pass = interior ? 3 : 4;
-      if (interior) prefix = (bucket + 4096u + ((127u - 12u) << 4)) << 19;
-      for (int pass = 0; pass < n_pass; ++pass) {
-        const int shift = interior ? (pass == 0 ? 11 : (pass == 1 ? 3 : 0)) : 24 - 8 * pass;
-        const int bits = (interior && pass == 2) ? 3 : 8;
-        const uint32_t himask = (shift + bits >= 32) ? 0u : (0xffffffffu << (shift + bits));
-        uint32_t* lh = pass < 2 ? &sh.hist[1][pass][0] : &sh.tot[pass - 2][0];
-        for (int i = tid; i < total; i += kLossThreads) {
-          const uint32_t key = sh.gathered[i];
-          if ((key & himask) == prefix) {
-            const uint32_t bin = (key >> shift) & ((1u << bits) - 1u);
-            atomicAdd(&lh[bin >> 1], 1u << (16 * (bin & 1u)));
-          }
-        }
-        __syncthreads();
-        const int bin = find_bin_desc(lh, rem, lane);
-        prefix |= static_cast<uint32_t>(bin) << shift;
-      }
-      }
-    } else {
-      // fallback (a bucket with more than kGatherCap candidates, e.g. thousands of identical CEs):
-      // cluster-wide 4-pass radix select on the full key through distributed shared memory
-      for (int i = tid; i < 2 * 2 * 128; i += kLossThreads) (&sh.hist[0][0][0])[i] = 0u;
-      __syncthreads();
-      rem = static_cast<uint32_t>(sel_set == 0 ? sh.k_pos : sh.k_neg);
-      for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        const int buf = pass & 1;
-        const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-          if (s * kBlockRows >= my_rows_w) continue;
-          const uint32_t key = float_key(ce[s]);
-          const bool member = valid[s] && (((mlo[s] | mhi[s]) != 0u) == (sel_set == 0)) && ((key & himask) == prefix);
-          hist_add(&sh.hist[buf][0][0], member, sel_set, (key >> shift) & 255u, lane);
-        }
-        cluster.sync();
-        if (tid < 128) {
-          uint32_t t = 0;
-#pragma unroll
-          for (int r = 0; r < kCluster; ++r) t += *cluster.map_shared_rank(&sh.hist[buf][sel_set][tid], r);
-          sh.tot[0][tid] = t;
-        } else if (tid < 384) {
-          (&sh.hist[buf ^ 1][0][0])[tid - 128] = 0u;
-        }
-        __syncthreads();
-        const int bin = find_bin_desc(sh.tot[0], rem, lane);
-        prefix |= static_cast<uint32_t>(bin) << shift;
-        __syncthreads();
-      }
-    }
-    sel_key = prefix;
-    if (tid == 0) sh.overflow = over;
-  }
-  cluster_arrive_nodata();      // last access to distributed shared memory is behind us; the matching wait is at kernel end
-  trace_point_t<kTrace>(p, 8);
-  const float thr_sel = need_select ? key_float(sel_key) : 0.0f;
-  const float thr_pos = sel_set == 0 ? thr_sel : 0.0f;
-  const float thr_neg = sel_set == 1 ? thr_sel : 0.0f;
-  const int k_pos = sh.k_pos;
-  const float inv_pos = k_pos > 0 ? __fdiv_rn(1.0f, static_cast<float>(k_pos)) : 0.0f;     // ssd.py:226
-
-  // ---- masked sums (ssd.py:227) ---------------------------------------------------------------------------
-  // The CTA's partial goes to a global slot; the LAST of the image's CTAs to arrive (ticket) adds the partials in rank
-  // order -- deterministic, and nobody waits: the other CTAs go straight on to their gradient rows.
-  bool sel[kSlots];
-  asm volatile("griddepcontrol.wait;" ::: "memory");     // first global writes below: the previous grid (same workspace) is complete
-  {
-    float accf = 0.0f;
-    int cnt2 = 0;                            // selected positives | selected negatives << 16
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-      const bool pos = (mlo[s] | mhi[s]) != 0u;
-      sel[s] = valid[s] && (ce[s] > (pos ? thr_pos : thr_neg));
-      if (sel[s]) {
-        accf += pos ? (p.a * lloc[s] + ce[s]) : ce[s];
-        cnt2 += pos ? 1 : 65536;
-      }
-    }
-    const double acc = warp_sum(static_cast<double>(accf));
-    cnt2 = warp_sum(cnt2);
-    if (lane == 0) { sh.wred_loss[warp] = acc; sh.wred_a[warp] = cnt2; }
-    __syncthreads();
-    if (warp == kLossWarps - 1) {            // the warp with the least row work (none at all for P = 8732): the global
-                                             // round trips below stay off the other warps' gradient rows
-      double t = lane < kLossWarps ? sh.wred_loss[lane] : 0.0;
-      int c2 = lane < kLossWarps ? sh.wred_a[lane] : 0;
-      t = warp_sum(t);                      // fixed shuffle tree: deterministic
-      c2 = warp_sum(c2);
-      ImageSlot* slot = p.slots + n;
-      unsigned int arrived = 0u;
-      if (lane == 0) {
-        slot->part_loss[rank] = t;
-        slot->part_sel[rank] = c2;
-        __threadfence();
-        arrived = atomicAdd(&slot->ticket, 1u);
-      }
-      arrived = __shfl_sync(0xffffffffu, arrived, 0);
-      if (arrived == static_cast<unsigned int>(kCluster) - 1u) {       // last CTA of the image: the whole warp helps
-        __threadfence();
-        const double pl = lane < kCluster ? __ldcg(&slot->part_loss[lane]) : 0.0;
-        const int c = lane < kCluster ? __ldcg(&slot->part_sel[lane]) : 0;
-        double total = 0.0;
-#pragma unroll
-        for (int r = 0; r < kCluster; ++r) total += __shfl_sync(0xffffffffu, pl, r);      // rank order: deterministic
-        const int pos_sel = warp_sum(c & 0xffff), neg_sel = warp_sum(c >> 16);
-        unsigned int done = 0u;
-        if (lane == 0) {
-          slot->ticket = 0u;
-          const float li = static_cast<float>(total) * inv_pos;
-          if (p.stats) {
-            ssdh_image_stats st;
-            st.loss = li; st.thr_pos = thr_pos; st.thr_neg = thr_neg;
-            st.pos_raw = sh.pos_raw; st.k_pos = k_pos; st.k_neg = sh.k_neg; st.pos_sel = pos_sel; st.neg_sel = neg_sel;
-            p.stats[n] = st;
-          }
-          slot->image_loss = static_cast<double>(li);
-          __threadfence();
-          done = atomicAdd(p.ticket, 1u);
-        }
-        done = __shfl_sync(0xffffffffu, done, 0);
-        if (done == static_cast<unsigned int>(p.N) - 1u) {               // last image of the batch
-          __threadfence();
-          double acc = 0.0;                 // lane l adds images l, l + 32, ... in order, then a fixed shuffle tree
-          for (int i = lane; i < p.N; i += 32) acc += __ldcg(&p.slots[i].image_loss);
-          acc = warp_sum(acc);
-          if (lane == 0) {
-            *p.loss = static_cast<float>(acc * static_cast<double>(p.inv_n_global));
-            *p.ticket = 0u;
-          }
-        }
-      }
-    }
-  }
-  trace_point_t<kTrace>(p, 9);
-  // ---- gradient rows, in place over the slab, then out by TMA -------------------------------------------------
-  if (p.grad != nullptr) {
-    const float sn = inv_pos * p.inv_n_global;          // d loss / d (per-image sum)
-    float* img_out = p.grad + static_cast<size_t>(n) * p.P * row;
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-      if (s * kBlockRows >= my_rows_w) continue;                    // uniform per warp
-      float* rp = my_slab + static_cast<size_t>(s * kBlockRows + lane) * row;
-      // One code path for every lane: row <- scale * softmax(row) with scale = s_n * (sum of matched class weights)
-      // for a selected positive, s_n for a selected negative and 0 for an unselected row (exact zeros); then the
-      // one-hot corrections.  Warps without any selected row (the common case late in training) just clear.
-      if (!__any_sync(0xffffffffu, sel[s])) {
-        if (valid[s])
-          for (int c = 0; c < row; ++c) rp[c] = 0.0f;
-      } else if (valid[s]) {
-        const bool pos = (mlo[s] | mhi[s]) != 0u;
-        float tsum = 1.0f;
-        if (pos) {
-          if (!sh.soft_labels) {
-            tsum = static_cast<float>(__popc(mlo[s]) + __popc(mhi[s]));
-          } else {
-            tsum = 0.0f;
-            for (int half = 0; half < 2; ++half) {
-              uint32_t m = half ? mhi[s] : mlo[s];
-#pragma unroll 1
-              while (m) { tsum += gts[32 * half + __ffs(m) - 1].tsum; m &= m - 1; }
-            }
-          }
-        }
-        softmax_scaled<kC>(rp + 4, C, lse[s], sel[s] ? sn * tsum : 0.0f);
-        const float as = (sel[s] && pos) ? p.a * sn : 0.0f;       // offset columns of matched rows hold sum_g clamp(l - g_hat)
-        rp[0] *= as; rp[1] *= as; rp[2] *= as; rp[3] *= as;
-        if (sel[s]) {
-          if (!pos) {
-            rp[4] -= sn;
-          } else {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t m = half ? mhi[s] : mlo[s];
-              while (m) {
-                const int g = 32 * half + __ffs(m) - 1;
-                m &= m - 1;
-                const int label = gts[g].label;
-                if (label >= 0) {
-                  rp[4 + label] -= sn;
-                } else {
-                  const float* tw = p.targets + (static_cast<size_t>(n) * G + g) * row + 4;
-#pragma unroll 1
-                  for (int c = 0; c < C; ++c) rp[4 + c] -= sn * tw[c];      // soft labels: rare, kept small
-                }
-              }
-            }
-          }
-        }
-      }
-      const int rows_b = min(kBlockRows, my_rows_w - s * kBlockRows);
-      float* dst = img_out + (static_cast<size_t>(my_chunk) * kChunkRows + s * kBlockRows) * row;
-      const float* srcb = my_slab + static_cast<size_t>(s) * kBlockRows * row;
-      if (p.bulk) {
-        fence_async_smem();               // my generic-proxy writes -> visible to the TMA engine
-        __syncwarp();
-        if (lane == 0) {
-          bulk_store(dst, srcb, static_cast<uint32_t>(rows_b) * row * sizeof(float));
-          bulk_store_commit();
-        }
-      } else {
-        __syncwarp();
-#pragma unroll 1
-        for (int i = lane; i < rows_b * row; i += 32) dst[i] = srcb[i];
-      }
-    }
-  }
-
-  trace_point_t<kTrace>(p, 10);
-  if (p.bulk && p.grad != nullptr && lane == 0) bulk_store_wait();
-  cluster_wait_acquire();       // my shared memory may be read by cluster peers until they have all passed their selection
-  trace_point_t<kTrace>(p, 11);
-  trace_point_t<kTrace>(p, 12);
-  if (kTrace && p.trace != nullptr && tid == 0) {
-    unsigned int smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 13] = smid;
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 14] = t;
-    p.trace[static_cast<size_t>(blockIdx.x) * kTracePoints + 15] = static_cast<unsigned long long>(sh.overflow);
-  }
-}
-
 static unsigned long long* g_loss_trace = nullptr;
-
-static size_t loss_smem_bytes(int rows_per_cta, int row, int G) {
-  const size_t slab = (static_cast<size_t>(rows_per_cta) * row * sizeof(float) + 15) & ~static_cast<size_t>(15);
-  const size_t gt = (static_cast<size_t>(G) * sizeof(GtRec) + 15) & ~static_cast<size_t>(15);
-  return slab + gt + sizeof(LossShared);
 }
-
-static int chunks_for(int P) { return (P + kChunkRows - 1) / kChunkRows; }
-
-static int rows_per_cta_for(int P, int cluster) {          // shared-memory rows of the busiest CTA
-  return ((chunks_for(P) + cluster - 1) / cluster) * kChunkRows;
-}
-
-constexpr size_t kMaxDynSmem = 227 * 1024;
-
-// Which kernel shape serves (P, C, G): 4 CTAs x 768 threads when the quarter slab fits one SM, else 8 x 384.
-struct LossShape { int cluster, threads, rows_per_cta; size_t smem; };
-
-static bool pick_shape(int P, int C, int G, LossShape* out) {
-  static const int forced = [] { const char* e = getenv("SSDH_LOSS_CLUSTER"); return e ? atoi(e) : 0; }();
-  const int row = 4 + C;
-  const int shapes[2][2] = {{4, 768}, {8, 384}};
-  for (int i = 0; i < 2; ++i) {
-    if (forced && shapes[i][0] != forced) continue;
-    LossShape s;
-    s.cluster = shapes[i][0]; s.threads = shapes[i][1];
-    s.rows_per_cta = rows_per_cta_for(P, s.cluster);
-    s.smem = loss_smem_bytes(s.rows_per_cta, row, G);
-    if (s.rows_per_cta <= kSlots * s.threads && s.smem <= kMaxDynSmem) { *out = s; return true; }
-  }
-  return false;
-}
-
-template <int kC, int kT, int kCl, bool kTrace>
-static int launch_loss(const LossParams& p, size_t smem, cudaStream_t st) {
-  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<kC, kT, kCl, kTrace>), static_cast<int>(kMaxDynSmem), "ssdh_multibox_loss")) return e;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(p.N) * kCl);
-  cfg.blockDim = dim3(kT);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCl;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  static const int pdl = [] { const char* e = getenv("SSDH_LOSS_PDL"); return e ? atoi(e) : 1; }();
-  cfg.numAttrs = pdl ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, multibox_loss_kernel<kC, kT, kCl, kTrace>, p);
-  if (e != cudaSuccess) { set_error("ssdh_multibox_loss: launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
-  return 0;
-}
-
-template <int kC>
-static int launch_loss_shape(const LossParams& p, const LossShape& s, cudaStream_t st) {
-  // the instrumented build of the kernel (debug hook, see the bottom of this file) is a separate instantiation: the
-  // production kernel carries no trace code at all
-  if (p.trace != nullptr) {
-    if (s.cluster == 4) return launch_loss<kC, 768, 4, true>(p, s.smem, st);
-    return launch_loss<kC, 384, 8, true>(p, s.smem, st);
-  }
-  if (s.cluster == 4) return launch_loss<kC, 768, 4, false>(p, s.smem, st);
-  return launch_loss<kC, 384, 8, false>(p, s.smem, st);
-}
-
-}  // namespace ssdh
 
 using namespace ssdh;
 
@@ -1043,8 +16,9 @@ extern "C" size_t ssdh_multibox_loss_workspace_bytes(int N, int P, int C, int G)
 
 static int multibox_loss_impl(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
                               float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
-                              void* ws, size_t ws_bytes, ssdh_stream_t stream, const float* next_outputs, const float* next_targets,
-                              bool inputs_stable) {
+                              void* ws, size_t ws_bytes, ssdh_stream_t stream, const ssdh_loss_options& opt) {
+  const float* next_outputs = opt.next_outputs;
+  const float* next_targets = opt.next_targets;
   if (!outputs || !priors || !loss || N <= 0 || P <= 0 || C <= 0 || G < 0 || n_global <= 0 || (G > 0 && !targets)) {
     set_error("ssdh_multibox_loss: NULL pointer or non-positive dimension");
     return SSDH_E_ARG;
@@ -1078,24 +52,51 @@ static int multibox_loss_impl(const float* outputs, const float* targets, const 
   // TMA bulk copies need 16-byte aligned addresses and sizes for every (image, CTA, slot) chunk.
   const bool sizes_ok = (static_cast<long long>(P) * row) % 4 == 0;     // full blocks are 32 rows; only the tail block can be odd
   p.bulk = sizes_ok && aligned16(outputs) && (grad == nullptr || aligned16(grad));
-  p.early_inputs = inputs_stable ? 1 : 0;
+  p.early_inputs = opt.inputs_stable ? 1 : 0;
   p.trace = g_loss_trace;
+  p.ce_override = opt.ce_override;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (C == 21) return launch_loss_shape<21>(p, shape, st);
-  return launch_loss_shape<0>(p, shape, st);
+  const int mode = (opt.force_best_prior ? kModeForce : 0) | (opt.exact_math ? kModeExact : 0);
+  if (opt.ce_override && !opt.exact_math) { set_error("ssdh_multibox_loss_ex: ce_override is a hook of the exact_math test mode"); return SSDH_E_ARG; }
+  if (mode != 0) return launch_loss_extension(mode, p, shape, st);      // opt-in modes: loss_ext.cu
+  // the instrumented build of the kernel (debug hook, see the bottom of this file) is a separate instantiation: the
+  // production kernel carries no trace code at all
+  if (p.trace != nullptr) return launch_loss_mode<kModeTrace>(p, shape, st);
+  return launch_loss_mode<0>(p, shape, st);
+}
+
+static ssdh_loss_options default_options() {
+  ssdh_loss_options o = {};
+  o.struct_bytes = static_cast<uint32_t>(sizeof(ssdh_loss_options));
+  return o;
 }
 
 extern "C" int ssdh_multibox_loss(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
                                   float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
                                   void* ws, size_t ws_bytes, ssdh_stream_t stream) {
-  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, nullptr, nullptr, false);
+  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, default_options());
 }
 
 extern "C" int ssdh_multibox_loss_pipelined(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
                                             float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
                                             void* ws, size_t ws_bytes, ssdh_stream_t stream, const float* next_outputs,
                                             const float* next_targets) {
-  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, next_outputs, next_targets, true);
+  ssdh_loss_options o = default_options();
+  o.inputs_stable = 1;
+  o.next_outputs = next_outputs;
+  o.next_targets = next_targets;
+  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, o);
+}
+
+extern "C" int ssdh_multibox_loss_ex(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
+                                     float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,
+                                     void* ws, size_t ws_bytes, ssdh_stream_t stream, const ssdh_loss_options* options) {
+  if (!options) return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, default_options());
+  if (options->struct_bytes != sizeof(ssdh_loss_options)) {
+    set_error("ssdh_multibox_loss_ex: options->struct_bytes is %u, this build expects %zu", options->struct_bytes, sizeof(ssdh_loss_options));
+    return SSDH_E_ARG;
+  }
+  return multibox_loss_impl(outputs, targets, priors, N, P, C, G, a, thr, n_global, loss, grad, stats, ws, ws_bytes, stream, *options);
 }
 
 // Debug hook (not part of the public header): device buffer of [N * 8][16] u64 phase stamps, or NULL to disable.
@@ -1124,11 +125,11 @@ extern "C" int ssdh_device_info(int* sm_count, int* max_smem_optin, int* loss_cl
     cfg.attrs = attr; cfg.numAttrs = 1;
     int nc = 0;
     if (shape.cluster == 4) {
-      ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<21, 768, 4, false>), static_cast<int>(kMaxDynSmem), "ssdh_device_info");
-      e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 768, 4, false>, &cfg);
+      ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<21, 768, 4, 0>), static_cast<int>(kMaxDynSmem), "ssdh_device_info");
+      e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 768, 4, 0>, &cfg);
     } else {
-      ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<21, 384, 8, false>), static_cast<int>(kMaxDynSmem), "ssdh_device_info");
-      e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 384, 8, false>, &cfg);
+      ensure_dyn_smem(reinterpret_cast<const void*>(multibox_loss_kernel<21, 384, 8, 0>), static_cast<int>(kMaxDynSmem), "ssdh_device_info");
+      e = cudaOccupancyMaxActiveClusters(&nc, multibox_loss_kernel<21, 384, 8, 0>, &cfg);
     }
     if (e != cudaSuccess) { set_error("ssdh_device_info: occupancy: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return static_cast<int>(e); }
     *loss_max_active_clusters = nc;

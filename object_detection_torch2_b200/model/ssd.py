@@ -138,12 +138,14 @@ class SSD(nn.Module):
             yield from layer.parameters()
 
     # ---- head math: thin wrappers over the kernels ------------------------------------------------------------
-    def loss(self, outputs: torch.Tensor, targets: torch.Tensor, default_bboxes: torch.Tensor, a: int = 1) -> torch.Tensor:
-        """MultiBox loss, 0-dim, differentiable w.r.t. ``outputs`` (reference ssd.py:181-229): one fused launch."""
-        return ops.multibox_loss(outputs, targets, default_bboxes, a=a)
+    def loss(self, outputs: torch.Tensor, targets: torch.Tensor, default_bboxes: torch.Tensor, a: int = 1,
+             force_best_prior: bool = False) -> torch.Tensor:
+        """MultiBox loss, 0-dim, differentiable w.r.t. ``outputs`` (reference ssd.py:181-229): one fused launch.
+        ``force_best_prior`` is north_star's opt-in extension of the matching; off = the reference."""
+        return ops.multibox_loss(outputs, targets, default_bboxes, a=a, force_best_prior=force_best_prior)
 
-    def _match(self, gt: torch.Tensor, df: torch.Tensor, threshold: float = 0.25) -> torch.Tensor:
-        return ops.match(gt, df, threshold).mask
+    def _match(self, gt: torch.Tensor, df: torch.Tensor, threshold: float = 0.25, force_best_prior: bool = False) -> torch.Tensor:
+        return ops.match(gt, df, threshold, force_best_prior=force_best_prior).mask
 
     def _calc_delta(self, gt: torch.Tensor, df: torch.Tensor) -> torch.Tensor:
         return ops.encode(gt, df)

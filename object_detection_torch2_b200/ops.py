@@ -82,8 +82,11 @@ class MatchResult(NamedTuple):
 
 
 def match(gt: torch.Tensor, priors: torch.Tensor, threshold: float = 0.25, want_bits: bool = False, want_mask: bool = True,
-          want_best_gt: bool = False, want_best_prior: bool = False) -> MatchResult:
+          want_best_gt: bool = False, want_best_prior: bool = False, force_best_prior: bool = False) -> MatchResult:
+    """``force_best_prior`` (north_star extension, off = the reference): every real ground-truth box also claims the prior
+    ssdh_match reports as its arg-max IoU (lowest index on ties) when that IoU is positive."""
     lib = _lib.load()
+    want_best_prior = want_best_prior or force_best_prior
     _need_cuda(gt, priors)
     gt, priors = _f32c(gt), _f32c(priors)
     N, G, stride = gt.shape
@@ -99,6 +102,16 @@ def match(gt: torch.Tensor, priors: torch.Tensor, threshold: float = 0.25, want_
         with torch.cuda.device(dev):
             check(lib.ssdh_match(gt.data_ptr(), stride, N, G, priors.data_ptr(), P, float(threshold), _ptr(bits), _ptr(mask),
                                  _ptr(bg), _ptr(bi), _ptr(bp), _ptr(bpi), _stream()), "ssdh_match")
+    if force_best_prior and N > 0 and G > 0 and P > 0:
+        real = ((gt[:, :, 2] * gt[:, :, 3]) > 0) & (bpi > 0)
+        nn, gg = torch.nonzero(real, as_tuple=True)
+        rows = bp[nn, gg].long()
+        if mask is not None:
+            mask[nn, rows, gg] = True
+        if bits is not None:
+            add = torch.zeros_like(bits)
+            add.index_put_((nn, rows), torch.ones_like(gg, dtype=torch.int64) << gg, accumulate=True)     # distinct gt rows: sum == OR
+            bits |= add
     return MatchResult(bits, mask, bg, bi, bp, bpi)
 
 
@@ -181,12 +194,14 @@ def multibox_loss_raw(outputs: torch.Tensor, targets: torch.Tensor, priors: torc
                       n_global: Optional[int] = None, want_grad: bool = True, want_stats: bool = False,
                       loss_out: Optional[torch.Tensor] = None, grad_out: Optional[torch.Tensor] = None,
                       stats_out: Optional[torch.Tensor] = None, next_outputs: Optional[torch.Tensor] = None,
-                      next_targets: Optional[torch.Tensor] = None, inputs_stable: bool = False):
+                      next_targets: Optional[torch.Tensor] = None, inputs_stable: bool = False, force_best_prior: bool = False,
+                      exact_math: bool = False, ce_override: Optional[torch.Tensor] = None):
     """One launch: loss (0-d), d loss / d outputs (or None) and per-image stats (uint8 (N, 32) view of ssdh_image_stats, or None).
 
     Inputs must already be contiguous fp32 CUDA tensors (this is the graph-capturable hot call).  ``inputs_stable`` (implied
     by ``next_outputs`` / ``next_targets``): the caller vouches that the inputs were not written by the kernel that precedes
-    this call in the stream, see ssdh_multibox_loss_pipelined."""
+    this call in the stream, see ssdh_multibox_loss_pipelined.  ``force_best_prior`` (north_star extension, off = the
+    reference), ``exact_math`` and ``ce_override`` go through ssdh_multibox_loss_ex (see include/ssdhead.h)."""
     lib = _lib.load()
     _need_cuda(outputs, targets, priors)
     _check_loss_args(outputs, targets, priors, next_outputs, next_targets, loss_out, grad_out)
@@ -207,7 +222,15 @@ def multibox_loss_raw(outputs: torch.Tensor, targets: torch.Tensor, priors: torc
                 float(a), float(threshold), int(n_global or N), loss_out.data_ptr(),
                 _ptr(grad_out) if want_grad else None, _ptr(stats_out) if want_stats else None,
                 ws.data_ptr(), ws.numel(), _stream())
-        if next_outputs is None and next_targets is None and not inputs_stable:
+        if force_best_prior or exact_math or ce_override is not None:
+            _need_cuda(next_outputs, next_targets, ce_override)
+            if ce_override is not None and (ce_override.dtype != torch.float32 or tuple(ce_override.shape) != (N, P) or not ce_override.is_contiguous()):
+                raise ValueError("multibox_loss: ce_override must be a contiguous fp32 (N, P) tensor")
+            opt = _lib.LossOptions(ctypes.sizeof(_lib.LossOptions), int(bool(force_best_prior)),
+                                   int(bool(inputs_stable or next_outputs is not None or next_targets is not None)), int(bool(exact_math)),
+                                   _ptr(next_outputs), _ptr(next_targets), _ptr(ce_override))
+            check(lib.ssdh_multibox_loss_ex(*args, ctypes.byref(opt)), "ssdh_multibox_loss_ex")
+        elif next_outputs is None and next_targets is None and not inputs_stable:
             check(lib.ssdh_multibox_loss(*args), "ssdh_multibox_loss")
         else:                                   # L2 prefetch of the next micro-batch (same shapes) from inside the kernel
             _need_cuda(next_outputs, next_targets)
@@ -247,9 +270,10 @@ class _MultiBoxLossFn(torch.autograd.Function):
     """SSD.loss with its analytic gradient produced by the same launch as the forward value."""
 
     @staticmethod
-    def forward(ctx, outputs, targets, priors, a, threshold, n_global):
+    def forward(ctx, outputs, targets, priors, a, threshold, n_global, force_best_prior):
         want_grad = ctx.needs_input_grad[0]
-        loss, grad, _ = multibox_loss_raw(outputs, targets, priors, a, threshold, n_global, want_grad=want_grad)
+        loss, grad, _ = multibox_loss_raw(outputs, targets, priors, a, threshold, n_global, want_grad=want_grad,
+                                          force_best_prior=force_best_prior)
         ctx.grad = grad
         ctx.consumed = False
         return loss
@@ -259,7 +283,7 @@ class _MultiBoxLossFn(torch.autograd.Function):
     def backward(ctx, g):
         grad = ctx.grad
         if grad is None:
-            return (None,) * 6
+            return (None,) * 7
         if ctx.consumed:
             # the chain-rule factor is applied in place on the gradient the forward launch wrote (no second 28 MB buffer on
             # the hot path), so that buffer cannot serve a second backward
@@ -270,15 +294,16 @@ class _MultiBoxLossFn(torch.autograd.Function):
         g = _f32c(g.reshape(1))
         with torch.cuda.device(grad.device):
             check(lib.ssdh_scale_inplace(grad.data_ptr(), grad.numel(), g.data_ptr(), _stream()), "ssdh_scale_inplace")
-        return grad, None, None, None, None, None
+        return grad, None, None, None, None, None, None
 
 
 def multibox_loss(outputs: torch.Tensor, targets: torch.Tensor, priors: torch.Tensor, a: float = 1.0, threshold: float = 0.25,
-                  n_global: Optional[int] = None) -> torch.Tensor:
+                  n_global: Optional[int] = None, force_best_prior: bool = False) -> torch.Tensor:
     """Differentiable (w.r.t. ``outputs``) MultiBox loss, 0-dim tensor."""
     _need_cuda(outputs, targets, priors)
     o = outputs if (outputs.dtype == torch.float32 and outputs.is_contiguous()) else outputs.float().contiguous()
-    return _MultiBoxLossFn.apply(o, _f32c(targets.detach()), _f32c(priors.detach()), float(a), float(threshold), n_global)
+    return _MultiBoxLossFn.apply(o, _f32c(targets.detach()), _f32c(priors.detach()), float(a), float(threshold), n_global,
+                                 bool(force_best_prior))
 
 
 def prefetch_l2(t: torch.Tensor) -> None:

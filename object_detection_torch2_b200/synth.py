@@ -145,5 +145,11 @@ def plant_detections_device(outputs: torch.Tensor, targets: torch.Tensor, priors
             vals[:, 2] = torch.log(b[:, 2] / dp[:, 2])
             vals[:, 3] = torch.log(b[:, 3] / dp[:, 3])
             vals[torch.arange(nn.numel(), device=outputs.device), 4 + label[nn, gg]] = 6.0 - 1.5 * j
-            outputs[n0 + nn, r] = vals
+            # two boxes may pick the same prior: an indexed store with duplicate targets is not deterministic on the GPU,
+            # so only the first claimant (lowest image / box index) of every (image, prior) writes
+            key = nn * pr.shape[0] + r
+            order = torch.arange(key.numel(), device=key.device)
+            uniq, inv = torch.unique(key, return_inverse=True)
+            first = torch.full((uniq.numel(),), key.numel(), device=key.device, dtype=order.dtype).scatter_reduce(0, inv, order, reduce="amin")
+            outputs[n0 + nn[first], r[first]] = vals[first]
     return outputs

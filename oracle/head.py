@@ -80,12 +80,24 @@ def pair_iou_match(gt_box: torch.Tensor, priors: torch.Tensor) -> torch.Tensor:
     return torch.where(g_area > 0, iou, g_area.expand_as(iou))
 
 
-def match_mask(targets: torch.Tensor, priors: torch.Tensor, threshold: float = 0.25) -> torch.Tensor:
-    """(N, P, G) bool, ``iou > threshold`` with no best-prior forcing.  src/model/ssd.py:231-250."""
+def match_mask(targets: torch.Tensor, priors: torch.Tensor, threshold: float = 0.25,
+               force_best_prior: bool = False) -> torch.Tensor:
+    """(N, P, G) bool, ``iou > threshold``.  src/model/ssd.py:231-250 (the reference does NO best-prior forcing).
+
+    ``force_best_prior`` is the north_star extension, the identity when off: every real ground-truth
+    box (area > 0) additionally claims the prior it overlaps best (first maximum = lowest prior index on ties,
+    ``torch.argmax``), provided that best IoU is positive -- the SSD paper's "match each ground truth box to the default
+    box with the best jaccard overlap", expressed on the reference's multi-match mask."""
     N, G = targets.shape[0], targets.shape[1]
     out = torch.zeros(N, priors.shape[0], G, dtype=torch.bool)
     for g in range(G):
-        out[:, :, g] = pair_iou_match(targets[:, g, :4], priors) > threshold
+        iou = pair_iou_match(targets[:, g, :4], priors)
+        out[:, :, g] = iou > threshold
+        if force_best_prior:
+            best_iou, best_prior = iou.max(dim=1)
+            real = (targets[:, g, 2] * targets[:, g, 3] > 0) & (best_iou > 0)
+            rows = torch.nonzero(real).flatten()
+            out[rows, best_prior[rows], g] = True
     return out
 
 
@@ -133,7 +145,8 @@ def kplus1_threshold(values: torch.Tensor, k: int) -> torch.Tensor:
 # L4 + L7  MultiBox loss                                        src/model/ssd.py:181-229
 # ----------------------------------------------------------------------------------------
 def multibox_loss(outputs: torch.Tensor, targets: torch.Tensor, priors: torch.Tensor,
-                  a: float = 1.0, threshold: float = 0.25, want_grad: bool = False) -> Dict[str, torch.Tensor]:
+                  a: float = 1.0, threshold: float = 0.25, want_grad: bool = False,
+                  force_best_prior: bool = False) -> Dict[str, torch.Tensor]:
     """Restated ``SSD.loss``; returns the scalar and every per-image intermediate.
 
     Keys: loss (0-d), loss_per_image (N,), match (N,P,G) bool, pos_raw, k_pos, k_neg (N,) int64,
@@ -146,7 +159,7 @@ def multibox_loss(outputs: torch.Tensor, targets: torch.Tensor, priors: torch.Te
     loc = outputs[:, :, :4]
     logp = torch.log_softmax(outputs[:, :, 4:], dim=2)                  # ssd.py:298
 
-    match = match_mask(targets, priors, threshold)                      # ssd.py:199
+    match = match_mask(targets, priors, threshold, force_best_prior)    # ssd.py:199 (+ opt-in forcing, off = reference)
     l_loc = torch.zeros(N, P)
     ce_pos = torch.zeros(N, P)
     for g in range(G):
