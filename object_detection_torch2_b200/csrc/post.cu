@@ -217,10 +217,11 @@ struct NmsTile {                                   // the round's surviving cand
   float4 box[kTileC];                              // x1, x2, y1, y2
   float area[kTileC];
   int row[kTileC];
-  uint32_t mask[kTileC][kTileWords];               // mask[r] bit c (c > r): r suppresses c
+  uint32_t ov_in[kTileC][kTileWords];              // ov_in[c] bit r (r < c): the earlier (higher-score) survivor r overlaps c above the threshold
   uint8_t cls[kTileC];
   uint8_t alive[kTileC];
-  uint32_t alive_w[kTileWords], keep_w[kTileWords];
+  uint32_t alive_w[kTileWords], keep_w[kTileWords], supp_w[kTileWords];
+  int undecided[2];
   uint32_t alive_x[2][kNmsCluster][kTileWords];    // per round parity: every CTA's verdict on the round's candidates (written remotely)
 };
 
@@ -463,26 +464,35 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       // fast sweep: no per-pair branch; the band test needs positive finite areas on both sides (odd boxes are flagged
       // when they enter the kept list) and flags a borderline pair through `slack`; both cases redo the sweep exactly
       const bool tame = pt.usable && sh.odd_kept == 0 && me.area >= 1e-30f && me.area <= 1e30f;
-      float slack = 1.0f;
-      bool dead = false;
+      // Per pair two FMAs with exact signs: hi = inter - union * thr(1 + 2^-20), lo = inter - union * thr(1 - 2^-20).
+      // hi > 0: the rounded quotient is certainly above thr (suppressed); lo <= 0: certainly not; in between the pair is
+      // settled exactly below.  Both verdicts are accumulated as running maxima (no per-pair predicates), and only ONE of
+      // the two extents is clamped at zero: with w clamped, a negative h makes inter <= 0 and both values negative, the same
+      // verdict as the reference's doubly clamped product -- 16 instructions per pair instead of 23.
+      float acc_hi = -1.0f, acc_lo = -1.0f;
+      const float n_hi = -band.hi, n_lo = -band.lo;
       for (int j0 = 0; j0 < kept_local; j0 += 32 * kSplit) {
-        if (!__any_sync(0xffffffffu, alive && !dead)) break;
+        if (!__any_sync(0xffffffffu, alive && !(acc_hi > 0.0f))) break;
         const int j1 = min(j0 + 32 * kSplit, kept_local);
-        for (int j = j0 + part; j < j1; j += kSplit) {
+        int j = j0 + part;
+#pragma unroll 2
+        for (; j < j1; j += kSplit) {
           const float4 kb = k_box[j];
           const float wd = fmaxf(fminf(kb.y, me4.y) - fmaxf(kb.x, me4.x), 0.0f);
-          const float ht = fmaxf(fminf(kb.w, me4.w) - fmaxf(kb.z, me4.z), 0.0f);
+          const float ht = fminf(kb.w, me4.w) - fmaxf(kb.z, me4.z);
           const float inter = wd * ht;
           const float uni = (k_area[j] + me.area) - inter;
-          const float e = fmaf(uni, pt.nthr, inter), m = uni * pt.eps;
-          slack = fminf(slack, fabsf(e) - m);
-          bool hit = e > m;
-          if (kPerClass) hit = hit && (k_cls[j] == my_cls);
-          dead |= hit;
+          float hi = fmaf(uni, n_hi, inter), lo = fmaf(uni, n_lo, inter);
+          if (kPerClass) { const bool same = k_cls[j] == my_cls; hi = same ? hi : -1.0f; lo = same ? lo : -1.0f; }
+          acc_hi = fmaxf(acc_hi, hi);
+          acc_lo = fmaxf(acc_lo, lo);
         }
       }
-      if (__any_sync(0xffffffffu, alive && (!tame || !(slack > 0.0f)))) {     // rare: settle this candidate with the IEEE division
-        if (alive && (!tame || !(slack > 0.0f))) {
+      bool dead = acc_hi > 0.0f;
+      const bool maybe = acc_lo > 0.0f;
+      const bool redo = alive && (!tame || (maybe && !dead));
+      if (__any_sync(0xffffffffu, redo)) {     // rare: settle this candidate with the IEEE division
+        if (redo) {
           dead = false;
           for (int j = part; j < kept_local && !dead; j += kSplit) {
             bool hit = suppresses(k_box[j], k_area[j], me4, me.area);
@@ -537,50 +547,85 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
     __syncthreads();
     NMS_ACC(t_sweep, t_mark);
     const int Mw = (M + 31) >> 5;
+    // (2) mutual overlaps of the survivors, recorded at the SUPPRESSED side (sparse: a few hits per row): warp per earlier
+    // row r, lane per later column j
+    for (int i = tid; i < M * kTileWords; i += kNmsThreads) (&tile.ov_in[0][0])[i] = 0u;
+    if (tid < kTileWords) { tile.keep_w[tid] = 0u; tile.supp_w[tid] = 0u; }
+    if (tid < 2) tile.undecided[tid] = 0;
+    __syncthreads();
     for (int r = warp; r < M; r += kNmsWarps) {
       const float4 bi = tile.box[r];
       const float ai = tile.area[r];
       const int ci = tile.cls[r];
+      const uint32_t rbit = 1u << (r & 31);
       for (int w = r >> 5; w < Mw; ++w) {
         const int j = 32 * w + lane;
-        bool hit = false;
         if (j > r && j < M) {
-          hit = suppresses(bi, ai, tile.box[j], tile.area[j]);
+          const float4 bj = tile.box[j];
+          const float aj = tile.area[j];
+          const float wd = fmaxf(fminf(bi.y, bj.y) - fmaxf(bi.x, bj.x), 0.0f);
+          const float ht = fminf(bi.w, bj.w) - fmaxf(bi.z, bj.z);
+          const float inter = wd * ht;
+          const float uni = (ai + aj) - inter;
+          bool hit = fmaf(uni, -band.hi, inter) > 0.0f;                      // certain (see the sweep above)
+          const bool sure = hit || !(fmaf(uni, -band.lo, inter) > 0.0f);
+          const bool tame_pair = pt.usable && ai >= 1e-30f && ai <= 1e30f && aj >= 1e-30f && aj <= 1e30f;
+          if (!sure || !tame_pair) hit = suppresses(bi, ai, bj, aj);        // rare: band or odd boxes -> IEEE division
           if (kPerClass) hit = hit && (tile.cls[j] == ci);
+          if (hit) atomicOr(&tile.ov_in[j][r >> 5], rbit);
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) tile.mask[r][w] = word;
       }
     }
     __syncthreads();
     NMS_ACC(t_matrix, t_mark);
-    if (warp == 0) {
-      // word by word: the 32 rows of a word are settled on registers (lane l holds the bits of later rows of the SAME word
-      // that row l suppresses, fetched by shuffle), then the kept rows' masks are OR-ed into the later words
-      uint32_t removed = 0u, keepw = 0u;           // lane w < kTileWords holds word w
-      int total = kept_before;
-      for (int wr = 0; wr < Mw; ++wr) {
-        uint32_t cur = __shfl_sync(0xffffffffu, removed, wr);
-        const int r_mine = 32 * wr + lane;
-        const uint32_t intra = r_mine < M ? tile.mask[r_mine][wr] : 0u;
-        const int rows_here = min(32, M - 32 * wr);
-        uint32_t keptbits = 0u;
+    // (3) the sequential greedy rule (src/utils.py:102-108) as a parallel fixed point over the tile: survivor j is
+    //   suppressed as soon as an earlier overlapping survivor is known kept,
+    //   kept       as soon as every earlier overlapping survivor is known suppressed.
+    // The first undecided survivor in score order always resolves, so every round makes progress and the fixed point is
+    // exactly the sequential result; tiles settle in a handful of rounds instead of a 256-step walk on one warp.
+    {
+      int state = tid < M ? 0 : 2;             // 0 undecided, 1 kept, 2 suppressed / not a survivor
+      uint32_t in_w[kTileWords];
 #pragma unroll
-        for (int b = 0; b < 32; ++b) {
-          const uint32_t ib = __shfl_sync(0xffffffffu, intra, b);
-          const bool take = b < rows_here && !((cur >> b) & 1u) && total < limit;     // uniform
-          if (take) { keptbits |= 1u << b; cur |= ib; ++total; }
+      for (int w = 0; w < kTileWords; ++w) in_w[w] = (tid < M && w < Mw) ? tile.ov_in[tid][w] : 0u;
+      for (int round = 0; round <= M; ++round) {
+        if (state == 0) {
+          bool any_kept = false, all_supp = true;
+#pragma unroll
+          for (int w = 0; w < kTileWords; ++w) {
+            any_kept |= (in_w[w] & tile.keep_w[w]) != 0u;
+            all_supp &= (in_w[w] & ~tile.supp_w[w]) == 0u;
+          }
+          if (any_kept) state = 2;
+          else if (all_supp) state = 1;
         }
-        if (lane == wr) keepw = keptbits;
-        uint32_t todo = keptbits;
-        while (todo) {                             // uniform
-          const int r = 32 * wr + __ffs(todo) - 1;
-          todo &= todo - 1;
-          if (lane > wr && lane < Mw) removed |= tile.mask[r][lane];
+        __syncthreads();                        // everyone has read the word arrays (and the previous round's flag)
+        if (tid == 0) tile.undecided[(round + 1) & 1] = 0;
+        if (tid < M) {
+          const uint32_t bit = 1u << (tid & 31);
+          if (state == 1 && !(tile.keep_w[tid >> 5] & bit)) atomicOr(&tile.keep_w[tid >> 5], bit);
+          if (state == 2 && !(tile.supp_w[tid >> 5] & bit)) atomicOr(&tile.supp_w[tid >> 5], bit);
+          if (state == 0) tile.undecided[round & 1] = 1;
         }
+        __syncthreads();
+        if (!tile.undecided[round & 1]) break;  // block-uniform
       }
-      if (lane < kTileWords) tile.keep_w[lane] = keepw;
+    }
+    if (warp == 0) {
+      // top_k: only the first (limit - kept so far) kept survivors of the tile stay; totals for the next round
+      int cnt = lane < Mw ? __popc(tile.keep_w[lane]) : 0;
+      const int incl = warp_incl_scan(cnt, lane);
+      const int room = limit - kept_before;                       // > 0 here (the loop stops once the limit is reached)
+      const int before = incl - cnt;
+      if (lane < Mw && incl > room) {
+        uint32_t bits = tile.keep_w[lane], out = 0u;
+        int left = room - before;
+        while (bits && left > 0) { const uint32_t b = bits & (0u - bits); out |= b; bits ^= b; --left; }
+        tile.keep_w[lane] = out;
+      }
+      const int total_tile = __shfl_sync(0xffffffffu, incl, 31);
       if (lane == 0) {
+        const int total = kept_before + min(total_tile, room);
         sh.kept = total;
         if (total >= limit) sh.stop = 1;
       }

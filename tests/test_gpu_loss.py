@@ -493,16 +493,17 @@ def test_force_best_prior_loss(thr, scale, dist, priors_cpu, priors_gpu):
     sure = sel & ~near
     if bool(sure.any()):
         assert bool((g[:, :, :4].abs().sum(dim=2)[sure] > 0).all())
-        torch.testing.assert_close(g[sure], ref["grad"][sure], rtol=1e-4, atol=1e-9)
+        torch.testing.assert_close(g[sure], ref["grad"][sure], rtol=1e-4, atol=1e-5 * float(ref["grad"].abs().max()))
     # off = the reference, through the same entry point
     l0, g0, _ = ops.multibox_loss_raw(o.to(DEV), t.to(DEV).contiguous(), priors_gpu, threshold=thr)
     l1, g1, _ = ops.multibox_loss_raw(o.to(DEV), t.to(DEV).contiguous(), priors_gpu, threshold=thr, exact_math=False, force_best_prior=False)
     assert torch.equal(l0, l1) and torch.equal(g0, g1)
-    # public surface
-    net = SSD.__new__(SSD)
-    x = o.to(DEV).requires_grad_(True)
-    lf = net.loss(outputs=x, targets=t.to(DEV), default_bboxes=priors_gpu, force_best_prior=True)
-    np.testing.assert_allclose(float(lf), float(ref["loss"]), rtol=RTOL)
+    # public surface (SSD.loss matches at the reference's fixed 0.25, ssd.py:231)
+    if thr == 0.25:
+        net = SSD.__new__(SSD)
+        x = o.to(DEV).requires_grad_(True)
+        lf = net.loss(outputs=x, targets=t.to(DEV), default_bboxes=priors_gpu, force_best_prior=True)
+        np.testing.assert_allclose(float(lf.detach()), float(ref["loss"]), rtol=RTOL)
 
 
 # ------------------------------------------------------------------------------------------------------------------
