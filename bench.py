@@ -235,6 +235,8 @@ def main():
     ap.add_argument("--dist", default="D1", choices=["D1", "D2"])
     ap.add_argument("--no-extras", action="store_true", help="headline + e2e only (skip isolated / config3 / config4 / post / cpu legs)")
     ap.add_argument("--min-ms", type=float, default=MIN_TIMED_MS, help="minimum length of the timed window")
+    ap.add_argument("--collective", default="auto", choices=["auto", "nvlink", "nccl"],
+                    help="multi-GPU loss-scalar exchange: stores into the peers' inboxes from the loss kernel (nvlink) or a graph-captured ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -272,11 +274,23 @@ def main():
     losses = torch.zeros(GRAPH_STEPS, dtype=torch.float32, device=dev)
     reduced = torch.zeros(GRAPH_STEPS, dtype=torch.float32, device=dev)      # all-reduced losses of the PREVIOUS replay
 
+    # The step's only collective (the loss scalars).  Preferred: fused into the kernel -- the CTA that finalises a step stores
+    # its scalar into every rank's inbox over NVLink (csrc/exchange.cu), a tiny reduce kernel per replay adds them up.
+    xchg = None
+    if world > 1 and args.collective in ("auto", "nvlink"):
+        try:
+            xchg = parallel.ScalarExchange(dev)
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] NVLink scalar exchange unavailable ({exc}); using NCCL", file=sys.stderr)
+            if args.collective == "nvlink":
+                raise
+
     def step(k):
         # software pipelining: while batch i is on chip the kernel asks the L2 for batch i+1 (HBM is idle then)
         i, nxt = k % ROT, (k + 1) % ROT
         ops.multibox_loss_raw(outs[i], tgts[i], priors, a=1.0, threshold=0.25, n_global=n_global, want_grad=True,
-                              loss_out=losses[k], grad_out=grads[i], next_outputs=outs[nxt], next_targets=tgts[nxt])
+                              loss_out=losses[k], grad_out=grads[i], next_outputs=outs[nxt], next_targets=tgts[nxt], exchange=xchg)
 
     # One CUDA graph = GRAPH_STEPS consecutive steps cycling through the ROT buffer pairs.  With several GPUs the graph also
     # holds the step's only collective as a PARALLEL branch: the all-reduce of the previous replay's 48 loss scalars runs
@@ -284,7 +298,23 @@ def main():
     # for the next replay.
     collective = "none (1 GPU)"
     graph = None
-    if world > 1:
+    if xchg is not None:
+        side = torch.cuda.Stream(device=dev)
+
+        def body_x():
+            # parallel branch: rank-ordered sums of the PREVIOUS replay's 48 scalars (already in the inboxes); main branch: 48 steps,
+            # each publishing its scalar from the kernel's epilogue.  No collective launch, no host call.
+            cur = torch.cuda.current_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                xchg.reduce(GRAPH_STEPS, out=reduced)
+            for i in range(GRAPH_STEPS):
+                step(i)
+            cur.wait_stream(side)
+        graph = capture(ctx, body_x, warm=lambda: [step(i) for i in range(GRAPH_STEPS)])       # primes the inboxes with one replay's worth
+        collective = ("fused: the loss kernel's last CTA stores the step scalar into every rank's inbox over NVLink (st.relaxed.sys, 8 B per peer); "
+                      "one 64-thread reduce kernel per 48 steps as a parallel graph branch; no NCCL in the timed loop")
+    elif world > 1:
         dist.all_reduce(reduced)             # communicator set-up is not capturable
         torch.cuda.synchronize()
         side = torch.cuda.Stream(device=dev)
@@ -336,6 +366,12 @@ def main():
         fin = losses.clone()
         dist.all_reduce(fin)
         loss_value = float(fin.mean())
+        if xchg is not None:
+            # drain the last replay's scalars through the exchange and hold them against NCCL's sums of the same numbers
+            last = xchg.reduce(GRAPH_STEPS).clone()
+            torch.cuda.synchronize()
+            assert xchg.ok(), "scalar exchange: a peer never delivered"
+            assert torch.allclose(last, fin, rtol=1e-6, atol=0), "scalar exchange and ncclAllReduce disagree"
     else:
         loss_value = float(losses.mean())
     clocks = None

@@ -128,9 +128,36 @@ SSDH_API int ssdh_multibox_loss_pipelined(const float* outputs, const float* tar
  *                     IoU is positive.  0 = the reference.
  *   inputs_stable     the contract of ssdh_multibox_loss_pipelined.
  *   exact_math        libdevice exp / log and IEEE division instead of the approximate units (slower; for parity studies).
+ *   exchange          the step's scalar all-reduce fused into the kernel's epilogue (NVLink stores into the peers' inboxes).
  *   ce_override       test hook (needs exact_math): [N, P] cross-entropies the hard-negative selection is run on -- positive CE
  *                     for matched priors, negative CE for the others -- so the selection logic can be checked on the checker's
  *                     own numbers. */
+/* Step-scalar exchange over NVLink (the one collective of sharded training), see csrc/exchange.cu.
+ * Every rank owns an INBOX of world x SSDH_XCHG_RING 64-bit words (+ two 32-bit counters behind them) in device memory that
+ * its peers map through CUDA IPC.  When ssdh_multibox_loss_ex is given an exchange, the CTA that finalises step s stores
+ * (s << 32 | bits(loss)) into slot [rank][(s - 1) % ring] of EVERY rank's inbox -- one 8-byte store per peer over NVLink, no
+ * kernel launch, no NCCL.  ssdh_scalar_exchange_reduce(count) waits for the next `count` steps of all ranks and writes their
+ * sums (added in rank order: bit-identical on every rank) to out[count]; call it every <= ring / 2 steps, anywhere in the
+ * stream (it is CUDA-graph capturable; a peer that never delivers sets *status = 1 and yields NaN instead of hanging).
+ *   create:  allocates + zeroes this rank's inbox, returns it with its IPC handle (exchange the handles with any transport)
+ *   open:    maps a PEER's inbox (enables peer access lazily); close / destroy undo open / create. */
+#define SSDH_MAX_RANKS 16
+#define SSDH_XCHG_RING 256
+typedef struct ssdh_ipc_handle { unsigned char bytes[64]; } ssdh_ipc_handle;
+typedef struct ssdh_scalar_exchange {
+  int32_t world, rank;
+  uint32_t ring;                                  /* = SSDH_XCHG_RING */
+  uint32_t reserved;
+  unsigned long long* inbox[SSDH_MAX_RANKS];      /* inbox[r]: rank r's inbox as seen from THIS device (inbox[rank] = the local one) */
+  uint32_t* counters;                             /* local inbox + world * ring words: [0] steps pushed, [1] steps consumed */
+} ssdh_scalar_exchange;
+SSDH_API size_t ssdh_scalar_exchange_bytes(int world);
+SSDH_API int ssdh_scalar_exchange_create(int world, void** inbox, ssdh_ipc_handle* handle);
+SSDH_API int ssdh_scalar_exchange_open(const ssdh_ipc_handle* handle, void** peer_inbox);
+SSDH_API int ssdh_scalar_exchange_close(void* peer_inbox);
+SSDH_API int ssdh_scalar_exchange_destroy(void* inbox);
+SSDH_API int ssdh_scalar_exchange_reduce(const ssdh_scalar_exchange* x, int count, float* out, int* status, ssdh_stream_t stream);
+
 typedef struct ssdh_loss_options {
   uint32_t struct_bytes;       /* = sizeof(ssdh_loss_options) */
   int32_t force_best_prior;
@@ -139,6 +166,7 @@ typedef struct ssdh_loss_options {
   const float* next_outputs;   /* as in ssdh_multibox_loss_pipelined, may be NULL */
   const float* next_targets;
   const float* ce_override;    /* may be NULL */
+  const ssdh_scalar_exchange* exchange;   /* may be NULL: publish this step's loss scalar to every rank's inbox (see above) */
 } ssdh_loss_options;
 SSDH_API int ssdh_multibox_loss_ex(const float* outputs, const float* targets, const float* priors, int N, int P, int C, int G,
                        float a, float thr, int n_global, float* loss, float* grad, ssdh_image_stats* stats,

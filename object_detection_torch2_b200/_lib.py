@@ -19,10 +19,23 @@ class ImageStats(ctypes.Structure):
                 ("k_pos", c_int32), ("k_neg", c_int32), ("pos_sel", c_int32), ("neg_sel", c_int32)]
 
 
+MAX_RANKS, XCHG_RING = 16, 256
+
+
+class IpcHandle(ctypes.Structure):
+    _fields_ = [("bytes", ctypes.c_ubyte * 64)]
+
+
+class ScalarExchange(ctypes.Structure):
+    """Mirror of ``ssdh_scalar_exchange`` (include/ssdhead.h)."""
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("ring", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("inbox", c_void_p * MAX_RANKS), ("counters", c_void_p)]
+
+
 class LossOptions(ctypes.Structure):
     """Mirror of ``ssdh_loss_options`` (include/ssdhead.h)."""
     _fields_ = [("struct_bytes", ctypes.c_uint32), ("force_best_prior", c_int32), ("inputs_stable", c_int32), ("exact_math", c_int32),
-                ("next_outputs", c_void_p), ("next_targets", c_void_p), ("ce_override", c_void_p)]
+                ("next_outputs", c_void_p), ("next_targets", c_void_p), ("ce_override", c_void_p), ("exchange", POINTER(ScalarExchange))]
 
 
 # name -> (restype, argtypes); the single source the symbol test checks against the header
@@ -45,6 +58,12 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "ssdh_multibox_loss_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, POINTER(LossOptions)]),
+    "ssdh_scalar_exchange_bytes": (c_size_t, [c_int]),
+    "ssdh_scalar_exchange_create": (c_int, [c_int, POINTER(c_void_p), POINTER(IpcHandle)]),
+    "ssdh_scalar_exchange_open": (c_int, [POINTER(IpcHandle), POINTER(c_void_p)]),
+    "ssdh_scalar_exchange_close": (c_int, [c_void_p]),
+    "ssdh_scalar_exchange_destroy": (c_int, [c_void_p]),
+    "ssdh_scalar_exchange_reduce": (c_int, [POINTER(ScalarExchange), c_int, c_void_p, c_void_p, c_void_p]),
     "ssdh_scale_inplace": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "ssdh_prefetch_l2": (c_int, [c_void_p, c_size_t, c_void_p]),
     "ssdh_expand_targets": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -55,6 +55,17 @@ static int multibox_loss_impl(const float* outputs, const float* targets, const 
   p.early_inputs = opt.inputs_stable ? 1 : 0;
   p.trace = g_loss_trace;
   p.ce_override = opt.ce_override;
+  memset(&p.xchg, 0, sizeof(p.xchg));
+  if (opt.exchange) {
+    const ssdh_scalar_exchange& x = *opt.exchange;
+    if (x.world <= 0 || x.world > SSDH_MAX_RANKS || x.world > 32 || x.rank < 0 || x.rank >= x.world || x.ring == 0 || !x.counters) {
+      set_error("ssdh_multibox_loss_ex: malformed exchange (world %d, rank %d)", x.world, x.rank);
+      return SSDH_E_ARG;
+    }
+    for (int r = 0; r < x.world; ++r)
+      if (!x.inbox[r]) { set_error("ssdh_multibox_loss_ex: exchange inbox[%d] is NULL", r); return SSDH_E_ARG; }
+    p.xchg = x;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int mode = (opt.force_best_prior ? kModeForce : 0) | (opt.exact_math ? kModeExact : 0);
   if (opt.ce_override && !opt.exact_math) { set_error("ssdh_multibox_loss_ex: ce_override is a hook of the exact_math test mode"); return SSDH_E_ARG; }

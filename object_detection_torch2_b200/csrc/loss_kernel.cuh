@@ -76,6 +76,7 @@ struct LossParams {
                           //    may be read under that kernel's tail (programmatic dependent launch); 0: wait for it first
   unsigned long long* trace;   // debug: [grid][kTracePoints] SM clock stamps (NULL in production)
   const float* ce_override;    // kModeExact only: [N, P] cross-entropies to select on (positive CE of matched rows, negative CE of the others)
+  ssdh_scalar_exchange xchg;   // world == 0: off.  Otherwise the finalising CTA publishes the loss scalar to every rank's inbox
 };
 
 constexpr int kTracePoints = 64;
@@ -1048,9 +1049,22 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
           double acc = 0.0;                 // lane l adds images l, l + 32, ... in order, then a fixed shuffle tree
           for (int i = lane; i < p.N; i += 32) acc += __ldcg(&p.slots[i].image_loss);
           acc = warp_sum(acc);
+          const float batch_loss = static_cast<float>(acc * static_cast<double>(p.inv_n_global));
           if (lane == 0) {
-            *p.loss = static_cast<float>(acc * static_cast<double>(p.inv_n_global));
+            *p.loss = batch_loss;
             *p.ticket = 0u;
+          }
+          // The collective that follows the step, fused: lane r stores (step << 32 | loss bits) into rank r's inbox -- one 8-byte
+          // store per peer over NVLink (the local inbox included), value and step number in ONE word.
+          if (p.xchg.world > 0) {
+            uint32_t step = 0u;
+            if (lane == 0) { step = p.xchg.counters[0] + 1u; p.xchg.counters[0] = step; }
+            step = __shfl_sync(0xffffffffu, step, 0);
+            if (lane < p.xchg.world) {
+              unsigned long long* dst = p.xchg.inbox[lane] + static_cast<size_t>(p.xchg.rank) * p.xchg.ring + ((step - 1u) % p.xchg.ring);
+              const unsigned long long word = (static_cast<unsigned long long>(step) << 32) | __float_as_uint(batch_loss);
+              asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+            }
           }
         }
       }

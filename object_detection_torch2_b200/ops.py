@@ -195,13 +195,14 @@ def multibox_loss_raw(outputs: torch.Tensor, targets: torch.Tensor, priors: torc
                       loss_out: Optional[torch.Tensor] = None, grad_out: Optional[torch.Tensor] = None,
                       stats_out: Optional[torch.Tensor] = None, next_outputs: Optional[torch.Tensor] = None,
                       next_targets: Optional[torch.Tensor] = None, inputs_stable: bool = False, force_best_prior: bool = False,
-                      exact_math: bool = False, ce_override: Optional[torch.Tensor] = None):
+                      exact_math: bool = False, ce_override: Optional[torch.Tensor] = None, exchange=None):
     """One launch: loss (0-d), d loss / d outputs (or None) and per-image stats (uint8 (N, 32) view of ssdh_image_stats, or None).
 
     Inputs must already be contiguous fp32 CUDA tensors (this is the graph-capturable hot call).  ``inputs_stable`` (implied
     by ``next_outputs`` / ``next_targets``): the caller vouches that the inputs were not written by the kernel that precedes
     this call in the stream, see ssdh_multibox_loss_pipelined.  ``force_best_prior`` (north_star extension, off = the
-    reference), ``exact_math`` and ``ce_override`` go through ssdh_multibox_loss_ex (see include/ssdhead.h)."""
+    reference), ``exact_math``, ``ce_override`` and ``exchange`` (a ``parallel.ScalarExchange``: the step's loss scalar is stored into every
+    rank's inbox over NVLink by the kernel itself) go through ssdh_multibox_loss_ex (see include/ssdhead.h)."""
     lib = _lib.load()
     _need_cuda(outputs, targets, priors)
     _check_loss_args(outputs, targets, priors, next_outputs, next_targets, loss_out, grad_out)
@@ -222,13 +223,14 @@ def multibox_loss_raw(outputs: torch.Tensor, targets: torch.Tensor, priors: torc
                 float(a), float(threshold), int(n_global or N), loss_out.data_ptr(),
                 _ptr(grad_out) if want_grad else None, _ptr(stats_out) if want_stats else None,
                 ws.data_ptr(), ws.numel(), _stream())
-        if force_best_prior or exact_math or ce_override is not None:
+        if force_best_prior or exact_math or ce_override is not None or exchange is not None:
             _need_cuda(next_outputs, next_targets, ce_override)
             if ce_override is not None and (ce_override.dtype != torch.float32 or tuple(ce_override.shape) != (N, P) or not ce_override.is_contiguous()):
                 raise ValueError("multibox_loss: ce_override must be a contiguous fp32 (N, P) tensor")
             opt = _lib.LossOptions(ctypes.sizeof(_lib.LossOptions), int(bool(force_best_prior)),
                                    int(bool(inputs_stable or next_outputs is not None or next_targets is not None)), int(bool(exact_math)),
-                                   _ptr(next_outputs), _ptr(next_targets), _ptr(ce_override))
+                                   _ptr(next_outputs), _ptr(next_targets), _ptr(ce_override),
+                                   ctypes.pointer(exchange.desc) if exchange is not None else None)
             check(lib.ssdh_multibox_loss_ex(*args, ctypes.byref(opt)), "ssdh_multibox_loss_ex")
         elif next_outputs is None and next_targets is None and not inputs_stable:
             check(lib.ssdh_multibox_loss(*args), "ssdh_multibox_loss")

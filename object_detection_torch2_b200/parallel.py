@@ -78,6 +78,90 @@ class ScalarAllReducer:
         return torch.cat(rows) if rows else self.buf[:0].clone()
 
 
+class ScalarExchange:
+    """The step's scalar all-reduce without a collective launch (csrc/exchange.cu): every rank owns an inbox in device memory
+    that its peers map through CUDA IPC; ``ops.multibox_loss_raw(..., exchange=self)`` makes the loss kernel's last CTA store
+    the step's scalar into every rank's inbox over NVLink, and ``reduce(count)`` (one tiny kernel, CUDA-graph capturable)
+    returns the rank-ordered sums of the next ``count`` steps -- bit-identical on every rank.
+
+    torch.distributed is only the transport of the 64-byte IPC handles at construction.  Raises if CUDA IPC is not
+    available (callers fall back to ``ScalarAllReducer`` / NCCL)."""
+
+    def __init__(self, device, group=None):
+        import ctypes
+
+        from . import _lib
+        self._lib = lib = _lib.load()
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > _lib.MAX_RANKS:
+            raise ValueError(f"ScalarExchange supports up to {_lib.MAX_RANKS} ranks")
+        self._peers, self._inbox = [], None
+        with torch.cuda.device(self.device):
+            inbox, handle = ctypes.c_void_p(), _lib.IpcHandle()
+            _lib.check(lib.ssdh_scalar_exchange_create(self.world, ctypes.byref(inbox), ctypes.byref(handle)), "ssdh_scalar_exchange_create")
+            self._inbox = inbox.value
+            mine = torch.tensor(list(bytes(handle.bytes)), dtype=torch.uint8, device=self.device)
+            handles = [torch.zeros_like(mine) for _ in range(self.world)]
+            if self.world > 1:
+                dist.all_gather(handles, mine, group=group)
+            else:
+                handles[0] = mine
+            desc = _lib.ScalarExchange()
+            desc.world, desc.rank, desc.ring = self.world, self.rank, _lib.XCHG_RING
+            failed = 0
+            for r in range(self.world):
+                if r == self.rank:
+                    desc.inbox[r] = self._inbox
+                    continue
+                h = _lib.IpcHandle()
+                ctypes.memmove(h.bytes, bytes(handles[r].cpu().tolist()), 64)
+                ptr = ctypes.c_void_p()
+                if lib.ssdh_scalar_exchange_open(ctypes.byref(h), ctypes.byref(ptr)) != 0:
+                    failed = 1
+                    break
+                self._peers.append(ptr.value)
+                desc.inbox[r] = ptr.value
+            flag = torch.tensor([failed], device=self.device)
+            if self.world > 1:
+                dist.all_reduce(flag, group=group)                     # all ranks agree on whether the exchange is usable
+            if int(flag) != 0:
+                msg = lib.ssdh_last_error()
+                self.close()
+                raise RuntimeError(f"CUDA IPC is not available between the GPUs of this job ({msg.decode() if msg else 'peer failed'})")
+            desc.counters = self._inbox + self.world * _lib.XCHG_RING * 8
+            self.desc = desc
+            self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def reduce(self, count: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Sums over ranks of the next ``count`` steps' scalars (count <= ring / 2), on the current stream."""
+        import ctypes
+
+        from . import _lib
+        if out is None:
+            out = torch.empty(count, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.ssdh_scalar_exchange_reduce(ctypes.byref(self.desc), int(count), out.data_ptr(), self.status.data_ptr(),
+                                                             torch.cuda.current_stream().cuda_stream), "ssdh_scalar_exchange_reduce")
+        return out
+
+    def ok(self) -> bool:
+        """False if a ``reduce`` gave up on a peer (synchronises)."""
+        return int(self.status.item()) == 0
+
+    def close(self) -> None:
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for p in self._peers:
+                self._lib.ssdh_scalar_exchange_close(p)
+            self._peers = []
+            if self._inbox:
+                self._lib.ssdh_scalar_exchange_destroy(self._inbox)
+                self._inbox = None
+
+
 def all_reduce_tallies(tallies: torch.Tensor, group=None) -> torch.Tensor:
     """Exact integer sum of the (C-1, 3) TP / detection / ground-truth tallies over all ranks (in place)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

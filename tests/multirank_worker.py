@@ -62,6 +62,30 @@ def main():
     check(rows.shape == (3, 2) and all(abs(float(rows[k, 0]) - (k + 1) * float(loss_1)) <= 2e-6 * abs(float(loss_1)) for k in range(3))
           and rows[:, 1].tolist() == [float(N)] * 3, "ScalarAllReducer rows are wrong")
 
+    # the same scalars through the NVLink exchange fused into the loss kernel (csrc/exchange.cu): rank-ordered sums, identical
+    # on every rank bit for bit, equal to the all-reduced loss
+    try:
+        xchg = parallel.ScalarExchange(dev)
+    except RuntimeError as exc:
+        xchg = None
+        if rank == 0:
+            print(f"scalar exchange skipped: {exc}", flush=True)
+    if xchg is not None:
+        want = []
+        for k in range(5):
+            sub = slice(k, k + 4)
+            l_k, _, _ = ops.multibox_loss_raw(so[sub].contiguous(), st[sub].contiguous(), priors, n_global=N, want_grad=False, exchange=xchg)
+            want.append(parallel.global_loss(l_k))
+        got = xchg.reduce(5)
+        torch.cuda.synchronize()
+        check(xchg.ok(), "scalar exchange gave up on a peer")
+        check(torch.allclose(got, torch.stack(want), rtol=1e-6, atol=0), f"scalar exchange {got.tolist()} vs all-reduce {[float(w) for w in want]}")
+        everyone = [torch.zeros_like(got) for _ in range(world)]
+        dist.all_gather(everyone, got)
+        check(all(torch.equal(e, everyone[0]) for e in everyone), "exchange sums are not bit-identical across ranks")
+        dist.barrier()
+        xchg.close()
+
     # ---- evaluation ------------------------------------------------------------------------------------------------
     t2 = synth.make_targets(N, 78)
     o2 = synth.plant_detections(synth.make_outputs(N, 78, "D2"), t2, priors.cpu(), 78).to(dev)
