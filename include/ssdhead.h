@@ -252,6 +252,16 @@ SSDH_API int ssdh_eval_accumulate_kept(const float* outputs, const int32_t* keep
  * entry point that synchronises (4 bytes device -> host on `stream`); call it once after the last batch. */
 SSDH_API int ssdh_eval_status(const void* ws, int* status_host, ssdh_stream_t stream);
 
+/* "Next" row: the true PASCAL VOC average precision, opt-in beside the reference's recall-style AP
+ * (src/evaluate.py:45-67 collapses to TP / #gt, see the tallies above).  One (score, tp flag, class) triple per detection of
+ * the whole dataset (tp: 1 = true positive, anything else = false positive, as tp_flags of ssdh_eval_accumulate; cls: 0-based
+ * non-void class), D of them, and the tallies [NC, 3] for the per-class ground-truth counts.  Detections are ranked per class
+ * by descending score (ties: input order); ap_out [NC] = area under the monotone precision envelope (VOC2010+) or the
+ * 11-point mean (use_07_metric), NaN for classes without ground truth.  fp64 inside, as the host restatement. */
+SSDH_API size_t ssdh_voc_ap_workspace_bytes(int D, int NC);
+SSDH_API int ssdh_voc_ap(const float* scores, const uint8_t* tp, const int32_t* cls, int D, const int64_t* tallies, int NC,
+                int use_07_metric, float* ap_out, void* ws, size_t ws_bytes, ssdh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,8 @@ SIGNATURES = {
     "ssdh_eval_accumulate_kept": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                           c_void_p, c_void_p, c_size_t, c_void_p]),
     "ssdh_eval_status": (c_int, [c_void_p, POINTER(c_int), c_void_p]),
+    "ssdh_voc_ap_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ssdh_voc_ap": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

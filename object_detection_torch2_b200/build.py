@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssdhead.so")
-SOURCES = ["runtime.cu", "priors.cu", "match.cu", "loss.cu", "loss_ext.cu", "post.cu", "eval.cu", "pack.cu", "exchange.cu"]
+SOURCES = ["runtime.cu", "priors.cu", "match.cu", "loss.cu", "loss_ext.cu", "post.cu", "eval.cu", "pack.cu", "exchange.cu", "vocap.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
          "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static", "--threads", "0"]
 

@@ -53,7 +53,8 @@ def voc_average_precision(scores: torch.Tensor, tp: torch.Tensor, n_gt: int, use
     """PASCAL VOC AP of one class from its detections over the WHOLE dataset: ``scores`` (D,), ``tp`` (D,) 0/1 flags
     (first-claimant assignment, as the kernel produces them), ``n_gt`` ground-truth boxes.  Detections are ranked
     jointly by score (stable: earlier entries first on ties); AP is the 11-point mean (VOC2007) or the area under the
-    monotone precision envelope (VOC2010+).  Pure tensor math, runs wherever the inputs live."""
+    monotone precision envelope (VOC2010+).  Pure tensor math, runs wherever the inputs live: the host-side restatement of
+    ``ops.voc_ap`` (the kernel ``DetectionEvaluator.compute`` uses), kept as its checker and for CPU-side callers."""
     if n_gt <= 0:
         return torch.tensor(float("nan"), device=scores.device)
     if scores.numel() == 0:
@@ -115,6 +116,6 @@ class DetectionEvaluator:
             packed = torch.cat([p[: int(k)] for p, k in zip(parts, sizes)])
             cls, score, tp = packed[:, 0].to(torch.int32), packed[:, 1], packed[:, 2]
         ap_ref = average_precision_from_tallies(tallies)
-        ap_voc = torch.stack([voc_average_precision(score[cls == c], tp[cls == c], int(tallies[c, 2]), use_07_metric)
-                              for c in range(self.num_classes)])
+        # one stable radix sort + one CTA per class (ssdh_voc_ap); ``voc_average_precision`` above is its host restatement
+        ap_voc = ops.voc_ap(score, tp, cls, tallies, use_07_metric)
         return dict(tallies=tallies, ap_reference=ap_ref, ap_voc=ap_voc)

@@ -545,3 +545,26 @@ def eval_status(device) -> None:
             ws[:4].zero_()
             raise _lib.SsdHeadError("ssdh_eval_accumulate: an image had more than P positive score entries (rows with several "
                                     "positive classes); detections were dropped.  Feed calc_score / postprocess output.")
+
+
+# ------------------------------------------------------------------------------------------------ 8f-4 true VOC AP
+def voc_ap(scores: torch.Tensor, tp: torch.Tensor, cls: torch.Tensor, tallies: torch.Tensor, use_07_metric: bool = False) -> torch.Tensor:
+    """PASCAL VOC AP per class on the device (ssdh_voc_ap): ``scores`` (D,) fp32, ``tp`` (D,) 1 = true positive, ``cls`` (D,)
+    0-based class, ``tallies`` (C-1, 3) int64 (ground-truth counts in column 2) -> (C-1,) fp32, NaN without ground truth."""
+    lib = _lib.load()
+    _need_cuda(scores, tp, cls, tallies)
+    D = int(scores.numel())
+    NC = int(tallies.shape[0])
+    if tp.numel() != D or cls.numel() != D or tallies.dim() != 2 or tallies.shape[1] != 3 or tallies.dtype != torch.int64:
+        raise ValueError("voc_ap: scores / tp / cls must have one entry per detection, tallies (C-1, 3) int64")
+    scores = _f32c(scores.reshape(-1))
+    tp8 = tp.reshape(-1).to(torch.uint8).contiguous()
+    cls32 = cls.reshape(-1).to(torch.int32).contiguous()
+    tallies = tallies.contiguous()
+    out = torch.empty(NC, dtype=torch.float32, device=tallies.device)
+    with torch.cuda.device(tallies.device):
+        ws = _workspace("vocap", lib.ssdh_voc_ap_workspace_bytes(D, NC), tallies.device)
+        check(lib.ssdh_voc_ap(scores.data_ptr() if D else None, tp8.data_ptr() if D else None, cls32.data_ptr() if D else None, D,
+                              tallies.data_ptr(), NC, int(bool(use_07_metric)), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+              "ssdh_voc_ap")
+    return out

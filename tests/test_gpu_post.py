@@ -387,3 +387,41 @@ def test_eval_overflow_is_reported():
     ok = torch.zeros(1, 64, 25, device=DEV)
     ok[0, :, 6] = 0.5
     evaluate.accumulate(ok, t)                                        # the status word was reset: the next call is clean
+
+
+@pytest.mark.gpu
+def test_voc_ap_kernel_matches_numpy_oracle():
+    """ssdh_voc_ap (one radix sort + one CTA per class) against the numpy restatement of the VOC devkit formula and the torch
+    restatement, both metrics: ties in score, classes without detections / without ground truth, segments longer than one
+    1024-wide chunk, all-TP and all-FP classes."""
+    g = torch.Generator().manual_seed(17)
+    NC = 20
+    sizes = [0, 1, 5, 300, 1024, 1025, 2500, 0, 40, 7, 64, 1, 2, 3, 900, 33, 0, 10, 4096, 12]
+    cls = torch.cat([torch.full((n,), c, dtype=torch.int32) for c, n in enumerate(sizes)])
+    D = cls.numel()
+    perm = torch.randperm(D, generator=g)
+    cls = cls[perm]
+    scores = torch.rand(D, generator=g)
+    scores[::7] = scores[3]                                       # plenty of exact ties: stable order decides
+    tp = (torch.rand(D, generator=g) > 0.55).to(torch.uint8)
+    tp[cls == 4] = 1                                              # all true positives
+    tp[cls == 5] = 0                                              # all false positives
+    tallies = torch.zeros(NC, 3, dtype=torch.int64)
+    tallies[:, 2] = torch.randint(1, 3000, (NC,), generator=g)
+    tallies[9, 2] = 0                                             # detections but no ground truth -> NaN
+    tallies[16, 2] = 0                                            # neither
+    for m07 in (False, True):
+        got = ops.voc_ap(scores.to(DEV), tp.to(DEV), cls.to(DEV), tallies.to(DEV), use_07_metric=m07).cpu()
+        for c in range(NC):
+            sel = cls == c
+            want = head.voc_ap_numpy(scores[sel].numpy(), tp[sel].float().numpy(), int(tallies[c, 2]), m07)
+            host = float(evaluate.voc_average_precision(scores[sel], tp[sel].float(), int(tallies[c, 2]), m07))
+            if np.isnan(want):
+                assert np.isnan(float(got[c])) and np.isnan(host), c
+            else:
+                assert float(got[c]) == pytest.approx(want, rel=1e-6, abs=1e-7), (c, m07, float(got[c]), want)
+                assert host == pytest.approx(want, rel=1e-6, abs=1e-7)
+    # no detections at all
+    empty = ops.voc_ap(torch.zeros(0, device=DEV), torch.zeros(0, dtype=torch.uint8, device=DEV), torch.zeros(0, dtype=torch.int32, device=DEV),
+                       tallies.to(DEV)).cpu()
+    assert torch.isnan(empty[9]) and float(empty[0]) == 0.0
