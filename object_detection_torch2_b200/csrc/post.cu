@@ -11,6 +11,7 @@
 //      same fp32 operation sequence as src/utils.py:74-77 so keep lists are bit-identical,
 //   D. score columns of rows that were not kept are zeroed (src/utils.py:114).
 #include <algorithm>
+#include <stdlib.h>
 
 #include <cooperative_groups.h>
 
@@ -23,26 +24,45 @@ namespace ssdh {
 // ------------------------------------------------------------------------------------------------
 // I1 / I2 row math shared by the stand-alone kernels and the fused pass (bitwise identical results)
 // ------------------------------------------------------------------------------------------------
+// exp(x) as 2^(x * log2 e): one rounded product + ex2.approx (2 ulp).  Relative error <= |x| * 6e-8 + 2.4e-7, i.e. < 2e-6 for
+// the |x| <= 20 a head produces -- inside the 1e-5 the decoded extents and scores are held to (north_star), and 5x fewer
+// instructions than libdevice's expf, which made this memory-bound pass issue-bound (ncu round 1: 56 % issue-active at 79 %
+// of the HBM roofline).  Index decisions (arg-max class, candidate order) never depend on it beyond the score values themselves.
+__device__ __forceinline__ float exp_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__fmul_rn(x, 1.4426950408889634f)));
+  return y;
+}
+
 __device__ __forceinline__ float4 decode_row(float p0, float p1, float p2, float p3, const float4 d) {
   float4 o;
   o.x = __fadd_rn(__fmul_rn(d.z, p0), d.x);        // src/utils.py:35
   o.y = __fadd_rn(__fmul_rn(d.w, p1), d.y);        // src/utils.py:36
-  o.z = __fmul_rn(d.z, expf(p2));                  // src/utils.py:37
-  o.w = __fmul_rn(d.w, expf(p3));                  // src/utils.py:38
+  o.z = __fmul_rn(d.z, exp_fast(p2));              // src/utils.py:37
+  o.w = __fmul_rn(d.w, exp_fast(p3));              // src/utils.py:38
   return o;
 }
 
-// softmax value at the arg-max class (first max wins) -- the only non-zero of the row, src/utils.py:54-55
+// softmax value at the arg-max class (first max wins) -- the only non-zero of the row, src/utils.py:54-55.
+// One routine for the stand-alone and the fused kernels (same operations in the same order: bitwise identical results).
 template <typename Load>
 __device__ __forceinline__ float best_score(Load logit, int C, int& best) {
   float mx = logit(0);
   best = 0;
+#pragma unroll
   for (int c = 1; c < C; ++c) {
     const float v = logit(c);
     if (v > mx) { mx = v; best = c; }
   }
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float nm = -__fmul_rn(mx, kLog2e);
   float sum = 0.0f;
-  for (int c = 0; c < C; ++c) sum += expf(logit(c) - mx);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(logit(c), kLog2e, nm)));
+    sum += e;
+  }
   return __fdiv_rn(1.0f, sum);
 }
 
@@ -86,9 +106,11 @@ iou_kernel(const float* __restrict__ t, int t_stride, int T, const float* __rest
 // ------------------------------------------------------------------------------------------------
 constexpr int kTileRows = 128;
 
+template <int kC>
 __global__ void __launch_bounds__(kTileRows)
-decode_score_kernel(float* __restrict__ outputs, const float4* __restrict__ priors, int P, int C, size_t total_rows,
+decode_score_kernel(float* __restrict__ outputs, const float4* __restrict__ priors, int P, int C_rt, size_t total_rows,
                     float* __restrict__ cand_key, uint8_t* __restrict__ cand_cls, int vec_ok) {
+  const int C = kC ? kC : C_rt;
   extern __shared__ __align__(16) float tile[];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // let the NMS grid get scheduled early (it waits below)
   const int row = 4 + C;
@@ -111,8 +133,17 @@ decode_score_kernel(float* __restrict__ outputs, const float4* __restrict__ prio
     while (pi >= P) pi -= P;
     const float4 box = decode_row(r[0], r[1], r[2], r[3], priors[pi]);
     int best;
-    const float s = best_score([&](int c) { return r[4 + c]; }, C, best);
+    float s;
+    if (kC > 0) {                                    // the VOC head: logits in registers, loops unrolled
+      float x[kC > 0 ? kC : 1];
+#pragma unroll
+      for (int c = 0; c < kC; ++c) x[c] = r[4 + c];
+      s = best_score([&](int c) { return x[c]; }, kC, best);
+    } else {
+      s = best_score([&](int c) { return r[4 + c]; }, C, best);
+    }
     r[0] = box.x; r[1] = box.y; r[2] = box.z; r[3] = box.w;
+#pragma unroll
     for (int c = 0; c < C; ++c) r[4 + c] = 0.0f;
     cand_key[grow] = best != 0 ? s : 0.0f;          // max over non-void columns, src/utils.py:99
     cand_cls[grow] = static_cast<uint8_t>(best);
@@ -1082,7 +1113,8 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   NmsWorkspace w;
   nms_ws_layout(N, P, ws, &w);
   const int row = 4 + C;
-  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_score_kernel), 96 * 1024, fn)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_score_kernel<21>), 96 * 1024, fn)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_score_kernel<0>), 96 * 1024, fn)) return e;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel<false, kNmsCluster>), 227 * 1024, fn)) return e;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_kernel<true, kNmsCluster>), 227 * 1024, fn)) return e;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(nms_small_kernel<false>), 100 * 1024, fn)) return e;
@@ -1130,8 +1162,10 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   // k+1 does not depend on nms_small(k) (different images), so with programmatic launch the memory-bound pass over part
   // k+1 runs on the same SMs under the compute-bound suppression of part k.  The very first launch is an ordinary one
   // (it depends on whatever produced `outputs`), and so is the final tiled kernel, which reads the flags of every part.
-  // Measured on B200 (batch 256): splitting is a loss -- three resident NMS CTAs per SM leave room for a single
-  // decode CTA, which starves the memory-bound pass -- so the batch goes through as one part.
+  // Measured on B200 (batch 256): splitting is a loss -- 131 us as one part, 148 / 189 / 222 us in 2 / 3 / 4 parts (round 2, with
+  // the lighter decode pass; 140 us in 2 parts when every kernel asks for the same shared-memory carve-out, which in turn
+  // costs the single-part chain 2 us): kernels with different carve-outs do not share an SM, so the parts mostly serialise
+  // and every extra launch adds its ramp -- the batch goes through as one part.
   const int parts = 1;
   for (int k = 0; k < parts; ++k) {
     const int n0 = static_cast<int>(static_cast<long long>(N) * k / parts), n1 = static_cast<int>(static_cast<long long>(N) * (k + 1) / parts);
@@ -1143,8 +1177,10 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
       const unsigned blocks = static_cast<unsigned>((rows_k + kTileRows - 1) / kTileRows);
       const size_t tile_bytes = static_cast<size_t>(kTileRows) * row * sizeof(float);
       const int vec_ok = aligned16(out_k) && ((static_cast<size_t>(kTileRows) * row) % 4 == 0);
-      if (int e = launch(decode_score_kernel, blocks, kTileRows, tile_bytes, k > 0, out_k, reinterpret_cast<const float4*>(priors), P, C, rows_k,
-                         w.cand_key + off, w.cand_cls + off, vec_ok)) return e;
+      if (int e = C == 21 ? launch(decode_score_kernel<21>, blocks, kTileRows, tile_bytes, k > 0, out_k, reinterpret_cast<const float4*>(priors), P, C, rows_k,
+                                   w.cand_key + off, w.cand_cls + off, vec_ok)
+                          : launch(decode_score_kernel<0>, blocks, kTileRows, tile_bytes, k > 0, out_k, reinterpret_cast<const float4*>(priors), P, C, rows_k,
+                                   w.cand_key + off, w.cand_cls + off, vec_ok)) return e;
     } else {
       const unsigned blocks = static_cast<unsigned>(std::min<size_t>((rows_k + 7) / 8, 148 * 16));
       if (int e = launch(candidate_kernel, blocks, 256, 0, k > 0, static_cast<const float*>(out_k), C, rows_k, w.cand_key + off, w.cand_cls + off)) return e;
@@ -1161,8 +1197,10 @@ static int run_nms(float* outputs, const float* priors, int N, int P, int C, flo
   }
   cluster_dim = kNmsCluster;           // dense images: a cluster of CTAs each; 36 clusters (144 of the 148 SMs) walk over the batch
   const int dense_clusters = N < 36 ? N : 36;
-  if (per_class) return launch(nms_kernel<true, kNmsCluster>, static_cast<unsigned>(dense_clusters) * kNmsCluster, kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
-  return launch(nms_kernel<false, kNmsCluster>, static_cast<unsigned>(dense_clusters) * kNmsCluster, kNmsThreads, smem, false, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
+  // programmatic launch here too: the kernel's first statement is griddepcontrol.wait (everything before it in the stream is
+  // complete and visible), so only its launch latency and block scheduling overlap with the tail of its predecessor
+  if (per_class) return launch(nms_kernel<true, kNmsCluster>, static_cast<unsigned>(dense_clusters) * kNmsCluster, kNmsThreads, smem, parts == 1, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
+  return launch(nms_kernel<false, kNmsCluster>, static_cast<unsigned>(dense_clusters) * kNmsCluster, kNmsThreads, smem, parts == 1, p, static_cast<const int32_t*>(use_small ? w.large : nullptr));
 }
 
 }  // namespace ssdh
