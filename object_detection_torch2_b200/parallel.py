@@ -100,37 +100,46 @@ class ScalarExchange:
             raise ValueError(f"ScalarExchange supports up to {_lib.MAX_RANKS} ranks")
         self._peers, self._inbox = [], None
         with torch.cuda.device(self.device):
+            # Every step below is executed by EVERY rank whatever happened locally (a rank that cannot create or open an inbox
+            # still takes part in the collectives and reports through the flag), so a failure never strands the others.
             inbox, handle = ctypes.c_void_p(), _lib.IpcHandle()
-            _lib.check(lib.ssdh_scalar_exchange_create(self.world, ctypes.byref(inbox), ctypes.byref(handle)), "ssdh_scalar_exchange_create")
+            failed = 0
+            if lib.ssdh_scalar_exchange_create(self.world, ctypes.byref(inbox), ctypes.byref(handle)) != 0:
+                failed = 1
             self._inbox = inbox.value
             mine = torch.tensor(list(bytes(handle.bytes)), dtype=torch.uint8, device=self.device)
             handles = [torch.zeros_like(mine) for _ in range(self.world)]
+            flag = torch.tensor([failed], device=self.device)
             if self.world > 1:
                 dist.all_gather(handles, mine, group=group)
+                dist.all_reduce(flag, group=group)
             else:
                 handles[0] = mine
             desc = _lib.ScalarExchange()
             desc.world, desc.rank, desc.ring = self.world, self.rank, _lib.XCHG_RING
-            failed = 0
-            for r in range(self.world):
-                if r == self.rank:
-                    desc.inbox[r] = self._inbox
-                    continue
-                h = _lib.IpcHandle()
-                ctypes.memmove(h.bytes, bytes(handles[r].cpu().tolist()), 64)
-                ptr = ctypes.c_void_p()
-                if lib.ssdh_scalar_exchange_open(ctypes.byref(h), ctypes.byref(ptr)) != 0:
-                    failed = 1
-                    break
-                self._peers.append(ptr.value)
-                desc.inbox[r] = ptr.value
+            failed = int(flag)
+            if not failed:
+                for r in range(self.world):
+                    if r == self.rank:
+                        desc.inbox[r] = self._inbox
+                        continue
+                    h = _lib.IpcHandle()
+                    ctypes.memmove(h.bytes, bytes(handles[r].cpu().tolist()), 64)
+                    ptr = ctypes.c_void_p()
+                    if lib.ssdh_scalar_exchange_open(ctypes.byref(h), ctypes.byref(ptr)) != 0:
+                        failed = 1
+                        break
+                    self._peers.append(ptr.value)
+                    desc.inbox[r] = ptr.value
             flag = torch.tensor([failed], device=self.device)
             if self.world > 1:
                 dist.all_reduce(flag, group=group)                     # all ranks agree on whether the exchange is usable
             if int(flag) != 0:
                 msg = lib.ssdh_last_error()
+                if self.world > 1:
+                    dist.barrier(group=group)                          # nobody unmaps while a peer is still opening
                 self.close()
-                raise RuntimeError(f"CUDA IPC is not available between the GPUs of this job ({msg.decode() if msg else 'peer failed'})")
+                raise RuntimeError(f"CUDA IPC is not available between the GPUs of this job ({msg.decode() if msg else 'a peer failed'})")
             desc.counters = self._inbox + self.world * _lib.XCHG_RING * 8
             self.desc = desc
             self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
