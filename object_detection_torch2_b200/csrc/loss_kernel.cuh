@@ -118,6 +118,8 @@ struct ForceRecord {          // forcing exchange (kModeForce only; lives in the
 };
 static_assert(sizeof(HistRecord) % 16 == 0 && sizeof(ListRecord) % 16 == 0 && sizeof(ForceRecord) % 16 == 0, "records travel as 16-byte groups");
 static_assert(sizeof(ForceRecord) <= sizeof(ListRecord), "the forcing records alias the list records");
+static_assert(sizeof(ListRecord) >= 2 * 128 * sizeof(uint32_t), "the cluster-wide totals borrow my own list record's keys");
+static_assert(sizeof(HistRecord) >= kMaxLossWarps * (sizeof(double) + sizeof(int)), "the per-warp partial sums borrow a histogram record");
 
 template <int kCluster>
 struct LossSharedT {
@@ -126,13 +128,12 @@ struct LossSharedT {
                                       // are known, from[0].hist doubles as the second histogram buffer of the radix passes
   ListRecord lists[kCluster];         // [r]: candidates of rank r; my own slot is built in place, the others arrive by st.async;
                                       // afterwards the keys are compacted to the front of this array ("gathered")
-  uint32_t tot[2][128];               // cluster-wide packed totals
+  // (the cluster-wide totals, the counting / radix scratch of the selection and the per-warp partial sums have no storage of
+  // their own: each lives in an exchange record that is idle while it is needed -- see tot_a / scratch / wred_* in the kernel)
   unsigned long long mbar[kMaxLossWarps];   // one per warp: its 96-row chunk lands on it
   unsigned long long xbar[3];         // exchange barriers: histograms, candidate lists, forcing
   uint8_t gt_fast[kMaxGT], gt_slow[kMaxGT];          // ground-truth rows by matching path (see the match section)
   int n_fast, n_slow, soft_labels;
-  double wred_loss[kMaxLossWarps];
-  int wred_a[kMaxLossWarps];
   int pos_raw, k_pos, k_neg, sel_set, need_select, overflow;
   uint32_t sel_prefix, sel_rem;
   uint32_t force_any[2];              // kModeForce: ground-truth rows matched anywhere in the cluster
@@ -364,6 +365,17 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   GtRec* gts = reinterpret_cast<GtRec*>(smem_raw + slab_bytes);
   LossShared& sh = *reinterpret_cast<LossShared*>(smem_raw + slab_bytes + ((static_cast<size_t>(G) * sizeof(GtRec) + 15) & ~static_cast<size_t>(15)));
 
+  // Storage borrowed from exchange records while they are idle (their owners' phases never overlap with these uses):
+  //   tot_a    cluster-wide bucket totals [2][128], between exchange #1 and the list building, in MY OWN list record -- nobody
+  //            else ever writes lists[rank], and its counter word sits behind the 256 key words
+  //   scratch  256 words of counting / radix scratch for the selection and the fallback's totals, in from[1] (its peer's
+  //            histograms are consumed once the totals exist; from[0] is the second histogram buffer)
+  //   wred_*   per-warp partial sums of the masked-sum phase (after the selection), in from[2]
+  static_assert(kCluster >= 4, "the borrowed records from[1] and from[2] exist");
+  uint32_t* const tot_a = &sh.lists[rank].key[0];
+  uint32_t* const scratch = &sh.from[1].hist[0][0];
+  double* const wred_loss = reinterpret_cast<double*>(&sh.from[2]);
+  int* const wred_a = reinterpret_cast<int*>(wred_loss + kMaxLossWarps);
   const float* img_in = p.outputs + static_cast<size_t>(n) * p.P * row;
 
   // Programmatic dependent launch: let the NEXT grid in the stream be scheduled as soon as SMs free up.  It may run
@@ -800,7 +812,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     uint32_t t = sh.mine.hist[set][w];
 #pragma unroll
     for (int r = 0; r < kCluster - 1; ++r) t += sh.from[r].hist[set][w];
-    sh.tot[set][w] = t;
+    tot_a[set * 128 + w] = t;
   } else if (warp == 8) {
     int v = lane == 0 ? sh.mine.pos_local : (lane < kCluster ? sh.from[lane - 1].pos_local : 0);
     v = warp_sum(v);
@@ -820,7 +832,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     else if (k_neg < neg_raw) { set = 1; k = k_neg; }
     uint32_t rem = static_cast<uint32_t>(k);
     int bin = 0;
-    if (set >= 0) bin = find_bin_desc(sh.tot[set], rem, lane);
+    if (set >= 0) bin = find_bin_desc(tot_a + set * 128, rem, lane);
     if (lane == 0) {
       sh.k_pos = k_pos; sh.k_neg = k_neg;
       sh.sel_set = set; sh.need_select = set >= 0;
@@ -832,7 +844,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   // The local radix passes use from[0].hist (the peers' histograms are consumed) and tot[*] as their four zeroed
   // histograms; both are free from here on (the block barriers below order this clear before their reuse).
   uint32_t* const hist1 = &sh.from[0].hist[0][0];      // second histogram buffer: [2][128] words
-  if (tid < 256) { (&sh.tot[0][0])[tid] = 0u; hist1[tid] = 0u; }
+  if (tid < 256) { scratch[tid] = 0u; hist1[tid] = 0u; }
   trace_point_t<kTrace>(p, 7);
 
   const int sel_set = sh.sel_set;
@@ -895,7 +907,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
         // few candidates (the usual case): exact order statistic by counting, spread over the whole CTA.  With
         // above(v) = #{candidates > v}, the (rem+1)-th largest is the SMALLEST key whose above() is <= rem.  Thread t
         // compares candidate t % 256 with one part of the list and adds its partial count (tot[] is zero here).
-        uint32_t* cnt_above = &sh.tot[0][0];
+        uint32_t* cnt_above = scratch;
         constexpr int kParts = kLossThreads / 256;                 // 3 with 768 threads, 1 with 384
         const int ci = tid & 255, part = tid >> 8;
         if (tid == 0) sh.sel_prefix = 0xffffffffu;
@@ -927,7 +939,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
         const int shift = interior ? (pass == 0 ? 11 : (pass == 1 ? 3 : 0)) : 24 - 8 * pass;
         const int bits = (interior && pass == 2) ? 3 : 8;
         const uint32_t himask = (shift + bits >= 32) ? 0u : (0xffffffffu << (shift + bits));
-        uint32_t* lh = pass < 2 ? hist1 + 128 * pass : &sh.tot[pass - 2][0];
+        uint32_t* lh = pass < 2 ? hist1 + 128 * pass : scratch + 128 * (pass - 2);
         for (int i = tid; i < total; i += kLossThreads) {
           const uint32_t key = gathered[i];
           if ((key & himask) == prefix) {
@@ -964,12 +976,12 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
           uint32_t t = 0;
 #pragma unroll
           for (int r = 0; r < kCluster; ++r) t += *cluster.map_shared_rank(hbuf[buf] + sel_set * 128 + tid, r);
-          sh.tot[0][tid] = t;
+          scratch[tid] = t;
         } else if (tid < 384) {
           hbuf[buf ^ 1][tid - 128] = 0u;
         }
         __syncthreads();
-        const int bin = find_bin_desc(sh.tot[0], rem, lane);
+        const int bin = find_bin_desc(scratch, rem, lane);
         prefix |= static_cast<uint32_t>(bin) << shift;
         __syncthreads();
       }
@@ -1004,12 +1016,12 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     }
     const double acc = warp_sum(static_cast<double>(accf));
     cnt2 = warp_sum(cnt2);
-    if (lane == 0) { sh.wred_loss[warp] = acc; sh.wred_a[warp] = cnt2; }
+    if (lane == 0) { wred_loss[warp] = acc; wred_a[warp] = cnt2; }
     __syncthreads();
     if (warp == kLossWarps - 1) {            // the warp with the least row work (none at all for P = 8732): the global
                                              // round trips below stay off the other warps' gradient rows
-      double t = lane < kLossWarps ? sh.wred_loss[lane] : 0.0;
-      int c2 = lane < kLossWarps ? sh.wred_a[lane] : 0;
+      double t = lane < kLossWarps ? wred_loss[lane] : 0.0;
+      int c2 = lane < kLossWarps ? wred_a[lane] : 0;
       t = warp_sum(t);                      // fixed shuffle tree: deterministic
       c2 = warp_sum(c2);
       ImageSlot* slot = p.slots + n;
