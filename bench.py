@@ -592,7 +592,8 @@ def bench_config3(ctx):
     def body():
         for k in range(K):
             o, t, g = sets[k & 1]
-            ops.multibox_loss_raw(o, t, ctx.priors, n_global=BIG_BATCH, want_grad=True, loss_out=loss[k], grad_out=g)
+            # the two input sets are static: the launches may read them under their predecessor's tail (inputs_stable)
+            ops.multibox_loss_raw(o, t, ctx.priors, n_global=BIG_BATCH, want_grad=True, loss_out=loss[k], grad_out=g, inputs_stable=True)
     graph = capture(ctx, body)
     reps = 6
 

@@ -39,6 +39,24 @@ def test_library_exports_header_symbols():
     assert lib.ssdh_unpack_head(None, None, None, None, 1, 1, 25, 1, None) == -1
     assert lib.ssdh_expand_targets(None, None, 2, 3, 21, None, None) == -1
     assert lib.ssdh_expand_targets(None, None, 0, 3, 21, None, None) == 0         # nothing to do
+    # round-2 entry points: kept-list evaluation, VOC AP, extended loss, scalar exchange
+    assert lib.ssdh_eval_accumulate_kept(1, None, None, 1, 1, 8, 21, 1, 0.5, 1, None, 1, 256, None) == -1 and b"keep" in lib.ssdh_last_error()
+    assert lib.ssdh_eval_status(None, None, None) == -1
+    assert lib.ssdh_voc_ap(None, None, None, 5, None, 20, 0, None, None, 0, None) == -1
+    assert lib.ssdh_voc_ap(None, None, None, 0, 1, 300, 0, 1, None, 0, None) == -1            # more than 255 classes
+    opt = _lib.LossOptions()
+    opt.struct_bytes = 8                                                           # a caller built against another layout
+    assert lib.ssdh_multibox_loss_ex(1, 1, 1, 1, 8, 21, 1, 1.0, 0.25, 1, 1, None, None, 1, 1 << 20, None, ctypes.byref(opt)) == -1
+    assert b"struct_bytes" in lib.ssdh_last_error()
+    assert ctypes.sizeof(_lib.LossOptions) == 48 and ctypes.sizeof(_lib.ScalarExchange) == 16 + 8 * _lib.MAX_RANKS + 8
+    assert lib.ssdh_scalar_exchange_bytes(8) == 8 * _lib.XCHG_RING * 8 + 64 and lib.ssdh_scalar_exchange_bytes(0) == 0
+    assert lib.ssdh_scalar_exchange_bytes(_lib.MAX_RANKS + 1) == 0
+    assert lib.ssdh_scalar_exchange_reduce(None, 4, None, None, None) == -1
+    x = _lib.ScalarExchange()
+    x.world, x.rank, x.ring = 2, 0, _lib.XCHG_RING
+    assert lib.ssdh_scalar_exchange_reduce(ctypes.byref(x), 4, 1, None, None) == -1          # no counters / inboxes
+    assert lib.ssdh_scalar_exchange_create(0, None, None) == -1 and lib.ssdh_scalar_exchange_open(None, None) == -1
+    assert lib.ssdh_scalar_exchange_close(None) == 0 and lib.ssdh_scalar_exchange_destroy(None) == 0
 
 
 def test_stats_struct_layout():
