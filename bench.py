@@ -407,7 +407,7 @@ def main():
                        "launch": f"CUDA graph of {GRAPH_STEPS} steps, C ABI ssdh_multibox_loss_pipelined (in-kernel L2 prefetch of the next batch, programmatic dependent launch between steps)",
                        "timed_window": f">= {args.min_ms:.0f} ms of device time: {replays} graph replays = {steps} steps (--steps {args.steps} is the minimum)",
                        "parallelism": f"dp{world} (images sharded)", "collective": collective},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": steps, "clocks": clocks, "loss": loss_value,
+            "roofline": roofline, "e2e": e2e, "gpu_launches": steps + (replays if xchg is not None else 0), "clocks": clocks, "loss": loss_value,
             "timed_region_s": elapsed_ms * 1e-3}
 
     if not args.no_extras:
