@@ -79,7 +79,7 @@ struct LossParams {
   ssdh_scalar_exchange xchg;   // world == 0: off.  Otherwise the finalising CTA publishes the loss scalar to every rank's inbox
 };
 
-constexpr int kTracePoints = 64;
+constexpr int kTracePoints = 128;
 template <bool kTrace>
 __device__ __forceinline__ void trace_point_t(const LossParams& p, int idx) {
   if (kTrace && p.trace != nullptr && threadIdx.x == 0) {
@@ -132,8 +132,7 @@ struct LossSharedT {
   // their own: each lives in an exchange record that is idle while it is needed -- see tot_a / scratch / wred_* in the kernel)
   unsigned long long mbar[kMaxLossWarps];   // one per warp: its 96-row chunk lands on it
   unsigned long long xbar[3];         // exchange barriers: histograms, candidate lists, forcing
-  uint8_t gt_fast[kMaxGT], gt_slow[kMaxGT];          // ground-truth rows by matching path (see the match section)
-  int n_fast, n_slow, soft_labels;
+  int soft_labels;
   int pos_raw, k_pos, k_neg, sel_set, need_select, overflow;
   uint32_t sel_prefix, sel_rem;
   uint32_t force_any[2];              // kModeForce: ground-truth rows matched anywhere in the cluster
@@ -143,6 +142,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Warp-wide float minimum / maximum in one instruction (redux.sync on f32: sm_100a).
+__device__ __forceinline__ float warp_min_f32(float v) {
+  float r;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -401,8 +412,6 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   if (tid == 0) {
     sh.mine.pos_local = 0;
     sh.lists[rank].cnt = 0;
-    sh.n_fast = 0;
-    sh.n_slow = 0;
     sh.soft_labels = 0;
     // exchange barriers: one arrival (mine, with the byte count I expect from the peers) + the peers' transaction bytes
     mbar_init(&sh.xbar[0], 1);
@@ -414,6 +423,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     if (kForce) mbar_expect_tx(&sh.xbar[2], static_cast<uint32_t>(sizeof(ForceRecord)) * (kCluster - 1));
   }
   for (int i = tid; i < 2 * 128; i += kLossThreads) (&sh.mine.hist[0][0])[i] = 0u;
+  trace_point_t<kTrace>(p, 48);
   __syncthreads();
   // publish the barrier initialisation to the cluster; the matching wait sits behind the slab / ground-truth requests, where
   // the warps would be waiting for memory anyway
@@ -443,12 +453,14 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     for (int i = lane; i < my_rows_w * row; i += 32) my_slab[i] = src[i];
     __syncwarp();
   }
+  trace_point_t<kTrace>(p, 49);
   cluster_wait_acquire();      // every CTA of the cluster has initialised its exchange barriers (they all started together)
+  trace_point_t<kTrace>(p, 50);
 
   // ---- ground truth of this image -> shared: one warp per row, one coalesced request each -----------------
   for (int g = warp; g < G; g += kLossWarps) {
     const float* tr = p.targets + (static_cast<size_t>(n) * G + g) * row;
-    float box = 0.0f, tsum = 0.0f;
+    float box = 0.0f, csum = 0.0f;
     int nz = 0, ones = 0, label = -1;
     for (int base = 0; base < row; base += 32) {
       const int c = base + lane;
@@ -460,29 +472,31 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       nz += __popc(b_nz);
       ones += __popc(b_one);
       if (b_one) label = base + __ffs(b_one) - 1 - 4;
-      tsum += warp_sum(cls ? v : 0.0f);
+      csum += cls ? v : 0.0f;
     }
+    const bool one_hot = nz == 1 && ones == 1;
+    const float tsum = one_hot ? 1.0f : warp_sum(csum);             // a single 1 sums to exactly 1: no reduction needed
+    // lanes 2 / 3 hold w / h: both logarithms are taken side by side before lane 0 collects the record
+    const float lg = ((lane == 2 || lane == 3) && box > 0.0f) ? logf(box) : box;
     const float gcx = __shfl_sync(0xffffffffu, box, 0), gcy = __shfl_sync(0xffffffffu, box, 1);
     const float gw = __shfl_sync(0xffffffffu, box, 2), gh = __shfl_sync(0xffffffffu, box, 3);
+    const float lw = __shfl_sync(0xffffffffu, lg, 2), lh = __shfl_sync(0xffffffffu, lg, 3);
     if (lane == 0) {
       const Corners c = make_corners(gcx, gcy, gw, gh);
       GtRec r;
       r.x1 = c.x1; r.x2 = c.x2; r.y1 = c.y1; r.y2 = c.y2;
       r.area = c.area; r.cx = gcx; r.cy = gcy;
-      r.lw = gw > 0.0f ? logf(gw) : gw;
-      r.lh = gh > 0.0f ? logf(gh) : gh;
+      r.lw = lw;                                                     // log(w), or w itself when w <= 0 (ssd.py:269)
+      r.lh = lh;
       r.flags = (gw > 0.0f ? 1 : 0) | (gh > 0.0f ? 2 : 0);
-      r.label = (nz == 1 && ones == 1) ? label : -1;
+      r.label = one_hot ? label : -1;
       r.tsum = tsum;
       gts[g] = r;
-      // fast path: a normal positive area lets the band test decide IoU > thr without dividing; everything else
-      // (padding rows, degenerate or denormal boxes, exotic thresholds) takes the exact path
-      if (p.band.usable && c.area >= 1e-30f && c.area <= 1e30f) sh.gt_fast[atomicAdd(&sh.n_fast, 1)] = static_cast<uint8_t>(g);
-      else if (c.area > 0.0f || c.area > p.band.thr || !(c.area == c.area)) sh.gt_slow[atomicAdd(&sh.n_slow, 1)] = static_cast<uint8_t>(g);
       if (r.label < 0 && c.area > 0.0f) sh.soft_labels = 1;
     }
   }
-    // ---- corners of my priors and the outer bounds of my whole chunk (box around its priors, smallest / largest prior
+  trace_point_t<kTrace>(p, 51);
+  // ---- corners of my priors and the outer bounds of my whole chunk (box around its priors, smallest / largest prior
   // area), used below to drop ground-truth rows that cannot match ANY of them ------------------------------------
   Corners d[kSlots];
   float cb_x1 = 3e38f, cb_x2 = -3e38f, cb_y1 = 3e38f, cb_y2 = -3e38f, cb_amin = 3e38f, cb_amax = -3e38f;
@@ -497,12 +511,10 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
       tame = tame && pri[s].z > 0.0f && pri[s].w > 0.0f && pri[s].z < 1e18f && pri[s].w < 1e18f && fabsf(pri[s].x) < 1e18f && fabsf(pri[s].y) < 1e18f;
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    cb_x1 = fminf(cb_x1, __shfl_xor_sync(0xffffffffu, cb_x1, o)); cb_x2 = fmaxf(cb_x2, __shfl_xor_sync(0xffffffffu, cb_x2, o));
-    cb_y1 = fminf(cb_y1, __shfl_xor_sync(0xffffffffu, cb_y1, o)); cb_y2 = fmaxf(cb_y2, __shfl_xor_sync(0xffffffffu, cb_y2, o));
-    cb_amin = fminf(cb_amin, __shfl_xor_sync(0xffffffffu, cb_amin, o)); cb_amax = fmaxf(cb_amax, __shfl_xor_sync(0xffffffffu, cb_amax, o));
-  }
+  // warp-wide extremes: one CREDUX each on sm_100a instead of five shuffle rounds
+  cb_x1 = warp_min_f32(cb_x1); cb_x2 = warp_max_f32(cb_x2);
+  cb_y1 = warp_min_f32(cb_y1); cb_y2 = warp_max_f32(cb_y2);
+  cb_amin = warp_min_f32(cb_amin); cb_amax = warp_max_f32(cb_amax);
   tame = __all_sync(0xffffffffu, tame);
 
   __syncthreads();
@@ -520,37 +532,40 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   {
     const ThrBand band = p.band;
     const float nthr = -band.thr, eps = band.thr * 9.5367431640625e-07f;
-    const int n_fast = sh.n_fast, n_slow = sh.n_slow;
-    // Cull: lane i looks at fast row i (and i + 32).  IoU > thr needs inter * (1 + thr) > thr * (area_g + area_p), and
-    // inter can exceed neither the overlap of the row with the chunk's outer box nor either area; a row that fails this
-    // bound (with a 1e-4 safety margin, far above any rounding) for the chunk's extreme areas matches none of my priors.
-    uint32_t keep_lo = 0u, keep_hi = 0u;
+    // Which path a ground-truth row takes is decided per warp from the records themselves (lane g looks at rows g and
+    // g + 32).  Fast: a normal positive area lets the band test decide IoU > thr without dividing.  Slow: everything else
+    // that could still match (degenerate or denormal boxes, exotic thresholds); zero-padding rows take no path at all.
+    // Cull (fast rows only): IoU > thr needs inter * (1 + thr) > thr * (area_g + area_p), and inter can exceed neither the
+    // overlap of the row with the chunk's outer box nor either area; a row that fails this bound (with a 1e-4 safety
+    // margin, far above any rounding) for the chunk's extreme areas matches none of my priors.
+    uint32_t fast_lo = 0u, fast_hi = 0u, slow_lo = 0u, slow_hi = 0u, keep_lo = 0u, keep_hi = 0u;
     {
       const float thr = band.thr;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        if (half == 1 && n_fast <= 32) break;            // uniform
-        const int i = 32 * half + lane;
-        const bool have = i < n_fast;
-        const int g = have ? sh.gt_fast[i] : 0;
-        const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
-        const float garea = gts[g].area;
+        if (half == 1 && G <= 32) break;                 // uniform
+        const int g = 32 * half + lane;
+        const bool have = g < G;
+        const float4 q = *reinterpret_cast<const float4*>(&gts[have ? g : 0].x1);
+        const float garea = gts[have ? g : 0].area;
+        const bool fast = have && band.usable && garea >= 1e-30f && garea <= 1e30f;
+        const bool slow = have && !fast && (garea > 0.0f || garea > band.thr || !(garea == garea));
         const float w = fmaxf(fminf(q.y, cb_x2) - fmaxf(q.x, cb_x1), 0.0f);
         const float h = fmaxf(fminf(q.w, cb_y2) - fmaxf(q.z, cb_y1), 0.0f);
         const float imax = fminf(fminf(w * h, cb_amax), garea);
         const bool hopeless = imax * (1.0f + thr) <= thr * (garea + cb_amin) * 0.9999f;
-        const uint32_t k = __ballot_sync(0xffffffffu, have && !(tame && hopeless));
-        if (half == 0) keep_lo = k; else keep_hi = k;
+        const uint32_t f = __ballot_sync(0xffffffffu, fast), sl = __ballot_sync(0xffffffffu, slow);
+        const uint32_t k = __ballot_sync(0xffffffffu, fast && !(tame && hopeless));
+        if (half == 0) { fast_lo = f; slow_lo = sl; keep_lo = k; } else { fast_hi = f; slow_hi = sl; keep_hi = k; }
       }
     }
     float amb = 1.0f;                              // min over pairs of |e| - margin; <= 0 means "settle exactly"
     const int n_keep = __popc(keep_lo) + __popc(keep_hi);
 #pragma unroll 2
     for (int it = 0; it < n_keep; ++it) {
-      int i;
-      if (keep_lo) { i = __ffs(keep_lo) - 1; keep_lo &= keep_lo - 1; }
-      else { i = 32 + __ffs(keep_hi) - 1; keep_hi &= keep_hi - 1; }
-      const int g = sh.gt_fast[i];
+      int g;
+      if (keep_lo) { g = __ffs(keep_lo) - 1; keep_lo &= keep_lo - 1; }
+      else { g = 32 + __ffs(keep_hi) - 1; keep_hi &= keep_hi - 1; }
       const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
       const float garea = gts[g].area;
       const uint32_t bit = 1u << (g & 31);
@@ -580,10 +595,13 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     }
     // the band argument needs a positive union: chunks holding a prior of non-positive or non-finite extent settle exactly
     const bool unsure = !(amb > 0.0f) || !tame;
-    if (__any_sync(0xffffffffu, unsure) || n_slow > 0) {
-      const int n_exact = n_slow + (unsure ? n_fast : 0);
-      for (int i = 0; i < n_exact; ++i) {          // exact path: borderline pairs, exotic rows / thresholds
-        const int g = i < n_slow ? sh.gt_slow[i] : sh.gt_fast[i - n_slow];
+    if (__any_sync(0xffffffffu, unsure) || (slow_lo | slow_hi) != 0u) {
+      // exact path: borderline pairs (the thread redoes every fast row), exotic rows / thresholds
+      uint32_t ex_lo = slow_lo | (unsure ? fast_lo : 0u), ex_hi = slow_hi | (unsure ? fast_hi : 0u);
+      while (ex_lo | ex_hi) {
+        int g;
+        if (ex_lo) { g = __ffs(ex_lo) - 1; ex_lo &= ex_lo - 1; }
+        else { g = 32 + __ffs(ex_hi) - 1; ex_hi &= ex_hi - 1; }
         const float4 q = *reinterpret_cast<const float4*>(&gts[g].x1);
         const float garea = gts[g].area;
         const uint32_t bit = 1u << (g & 31);
@@ -854,17 +872,23 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     // my candidates of the selected bucket -> my list record (order is irrelevant)
     const uint32_t bucket = sh.sel_prefix;
     ListRecord& my_list = sh.lists[rank];
+    bool member[kSlots];
+    uint32_t ballot[kSlots];
+    int mine_n = 0;
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
-      if (s * kBlockRows >= my_rows_w) continue;                    // uniform per warp
-      const uint32_t key = float_key(ce[s]);
-      const bool member = valid[s] && (((mlo[s] | mhi[s]) != 0u) == (sel_set == 0)) && (bucket_of(key) == bucket);
-      const uint32_t ballot = __ballot_sync(0xffffffffu, member);
-      int base = 0;
-      if (lane == 0 && ballot) base = atomicAdd(&my_list.cnt, __popc(ballot));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      const int pos = base + __popc(ballot & lt_mask);
-      if (member && pos < kListCap) my_list.key[pos] = key;
+      member[s] = valid[s] && (((mlo[s] | mhi[s]) != 0u) == (sel_set == 0)) && (bucket_of(float_key(ce[s])) == bucket);
+      ballot[s] = __ballot_sync(0xffffffffu, member[s]);
+      mine_n += __popc(ballot[s]);
+    }
+    int base = 0;
+    if (lane == 0 && mine_n) base = atomicAdd(&my_list.cnt, mine_n);      // one reservation per warp
+    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+      const int pos = base + __popc(ballot[s] & lt_mask);
+      if (member[s] && pos < kListCap) my_list.key[pos] = float_key(ce[s]);
+      base += __popc(ballot[s]);
     }
     trace_point_t<kTrace>(p, 16);
     __syncthreads();                                  // my list record is complete

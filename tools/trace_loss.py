@@ -16,7 +16,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for _ in range(3):
     ops.multibox_loss_raw(o, t, priors)
 CL = ops.device_info()["loss_cluster_size"]
-trace = torch.zeros(N * CL, 64, dtype=torch.int64, device=dev)
+trace = torch.zeros(N * CL, 128, dtype=torch.int64, device=dev)
 flush.fill_(1)
 torch.cuda.synchronize()
 lib.ssdh_debug_set_loss_trace(trace.data_ptr())
@@ -28,7 +28,7 @@ torch.cuda.synchronize()
 lib.ssdh_debug_set_loss_trace(None)
 tr = trace.cpu().numpy()
 print("kernel ms", e0.elapsed_time(e1))
-names = ["start", "setup", "gt+tma issue", "match", "slab0 arrived", "rows done", "csync1", "gather0", "select done", "sums+csync2+finalize", "grad rows+stores issued", "stores read out", "end"]
+names = ["start", "setup", "gt+tma issue", "match", "slab0 arrived", "rows done", "csync1", "gather0", "select done", "sums+csync2", "grad+stores issued", "stores read out", "end"]
 clk = tr[:, 1:13].astype(np.float64)
 rel = (clk - clk[:, :1])
 g0, g1 = tr[:, 0], tr[:, 14]
@@ -41,7 +41,7 @@ for i, nm in enumerate(names[1:]):
     print("%-22s %10.0f %10.0f %10.0f   +%.0f" % (nm, np.median(col), np.percentile(col, 10), col.max(), np.median(col - prev)))
     prev = col
 sel = tr[:, 16:19].astype(np.float64) - clk[:, :1]
-print("select detail (median cycles since CTA start): list built %.0f, csync %.0f, gathered %.0f" % tuple(np.median(sel, axis=0)))
+print("select detail (median cycles since CTA start): list built %.0f, lists received %.0f, gathered %.0f" % tuple(np.median(sel, axis=0)))
 print("overflow fallbacks:", int(tr[:, 15].sum()))
 sm = tr[:, 13]
 cnt = np.bincount(sm.astype(int), minlength=148)

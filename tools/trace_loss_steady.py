@@ -13,7 +13,7 @@ for r in range(ROT):
 tgts = [torch.cat([t, torch.zeros(N, G - t.shape[1], 25)], 1).to(dev).contiguous() for t in tgts]
 outs = [o.to(dev) for o in outs]; grads = [torch.empty_like(o) for o in outs]; loss = torch.zeros(ROT, device=dev)
 CL = ops.device_info()["loss_cluster_size"]
-traces = [torch.zeros(N * CL, 64, dtype=torch.int64, device=dev) for _ in range(ROT)]
+traces = [torch.zeros(N * CL, 128, dtype=torch.int64, device=dev) for _ in range(ROT)]
 def step(i):
     lib.ssdh_debug_set_loss_trace(traces[i].data_ptr())
     nxt = (i + 1) % ROT
@@ -38,7 +38,9 @@ for i, nm in enumerate(names):
     print("%-22s median %8.0f  p10 %8.0f  max %8.0f   +%.0f" % (nm, np.median(col), np.percentile(col, 10), col.max(), np.median(col - prev)))
     prev = col
 sel = tr[:, 16:19].astype(np.float64) - clk[:, :1]
-print("select detail (median cycles since CTA start): list built %.0f, csync %.0f, gathered %.0f" % tuple(np.median(sel, axis=0)))
+print("select detail (median cycles since CTA start): list built %.0f, lists received %.0f, gathered %.0f" % tuple(np.median(sel, axis=0)))
+st = tr[:, 48:52].astype(np.float64) - clk[:, :1]
+print("startup detail (median): smem init %.0f, TMA issued %.0f, cluster wait done %.0f, ground truth parsed %.0f" % tuple(np.median(st, axis=0)))
 w = tr[:, 24:48].astype(np.float64) - clk[:, :1]
 print("row phase end per warp (median over CTAs, cycles since CTA start):", np.median(w, axis=0).astype(int).tolist())
 print("  per CTA: max over warps median %.0f, median over warps median %.0f" % (np.median(w.max(axis=1)), np.median(np.median(w, axis=1))))
