@@ -409,6 +409,9 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
     valid[s] = s * kBlockRows + lane < my_rows_w;
     pri[s] = __ldg(p.priors + (valid[s] ? grow : 0));
   }
+  // The (tiny) ground-truth rows are requested right away: their round trip is the longest chain of this prologue.
+  float gt_first = 0.0f;
+  if (warp < G) gt_first = __ldg(p.targets + (static_cast<size_t>(n) * G + warp) * row + min(lane, row - 1));
   if (tid == 0) {
     sh.mine.pos_local = 0;
     sh.lists[rank].cnt = 0;
@@ -428,10 +431,6 @@ __global__ void __launch_bounds__(kLossThreads, 1) multibox_loss_kernel(const Lo
   // publish the barrier initialisation to the cluster; the matching wait sits behind the slab / ground-truth requests, where
   // the warps would be waiting for memory anyway
   cluster_arrive_relaxed();
-
-  // The (tiny) ground-truth rows are requested first so they are not queued behind the slab traffic.
-  float gt_first = 0.0f;
-  if (warp < G) gt_first = __ldg(p.targets + (static_cast<size_t>(n) * G + warp) * row + min(lane, row - 1));
 
   // ---- slab: every warp fetches its own 96-row chunk with ONE TMA bulk copy onto its own mbarrier; issued right
   // behind the (tiny) ground-truth request, so that it lands while the ground truth is being unpacked -----------------
