@@ -786,10 +786,13 @@ __global__ void __launch_bounds__(kSmallThreads, 3) nms_small_kernel(const NmsPa
     mine += __popc(cand_bits[q]);
   }
   if (lane == 0) sh.warp_total[warp] = mine;
+  NMS_TRACE(12);
   for (int i = tid; i < kSmallCap * kSmallWords; i += kSmallThreads) (&sh.ov_in[0][0])[i] = 0u;
   if (tid < kSmallWords) { sh.kept_words[tid] = 0u; sh.supp_words[tid] = 0u; }
   if (tid < 2) sh.undecided[tid] = 0;
+  NMS_TRACE(13);
   __syncthreads();
+  NMS_TRACE(14);
   int before = 0, total = 0;
   for (int w = 0; w < kSmallWarps; ++w) {
     const int t = sh.warp_total[w];

@@ -17,4 +17,5 @@ names = ["A compaction", "B sort", "boxes", "C1 overlaps", "C2 fixed point", "D 
 for i, nm in enumerate(names):
     d = t[:, i + 1] - t[:, i]
     print(f"{nm:16s} median {np.median(d):8.0f}  p90 {np.percentile(d, 90):8.0f} cycles")
+print("A detail (median since start): keys loaded + ballots %.0f, ov_in cleared %.0f, barrier %.0f" % tuple(np.median(t[:, 12:15] - t[:, :1], axis=0)))
 print("total median", np.median(t[:, 6] - t[:, 0]), "rounds median", np.median(t[:, 8]), "max", t[:, 8].max())
