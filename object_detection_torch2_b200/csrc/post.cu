@@ -932,8 +932,27 @@ __global__ void __launch_bounds__(kSmallThreads, 3) nms_small_kernel(const NmsPa
         if (kPerClass) hit = hit && sh.cls[j] == ci;
         if (hit) atomicOr(&sh.ov_in[j][w0], ibit);
       };
+      // two words of columns per trip, both computed before either records its hits (independent chains: this loop is
+      // latency-bound, a CTA has 16 rows in flight)
+      auto pair2 = [&](int w) {
+        const int j0 = 32 * w + lane, j1 = j0 + 32;
+        const float4 b0 = sh.box[j0], b1 = sh.box[j1];
+        const float a0 = sh.area[j0], a1 = sh.area[j1];
+        const float wd0 = fmaxf(fminf(bi.y, b0.y) - fmaxf(bi.x, b0.x), 0.0f), wd1 = fmaxf(fminf(bi.y, b1.y) - fmaxf(bi.x, b1.x), 0.0f);
+        const float ht0 = fmaxf(fminf(bi.w, b0.w) - fmaxf(bi.z, b0.z), 0.0f), ht1 = fmaxf(fminf(bi.w, b1.w) - fmaxf(bi.z, b1.z), 0.0f);
+        const float in0 = wd0 * ht0, in1 = wd1 * ht1;
+        const float un0 = (ai + a0) - in0, un1 = (ai + a1) - in1;
+        const float e0 = fmaf(un0, pt.nthr, in0), m0 = un0 * pt.eps, e1 = fmaf(un1, pt.nthr, in1), m1 = un1 * pt.eps;
+        slack = fminf(slack, fminf(fabsf(e0) - m0, fabsf(e1) - m1));
+        bool hit0 = e0 > m0, hit1 = e1 > m1;
+        if (kPerClass) { hit0 = hit0 && sh.cls[j0] == ci; hit1 = hit1 && sh.cls[j1] == ci; }
+        if (hit0) atomicOr(&sh.ov_in[j0][w0], ibit);
+        if (hit1) atomicOr(&sh.ov_in[j1][w0], ibit);
+      };
       pair(w0, lane > (i & 31));
-      for (int w = w0 + 1; w < Kw; ++w) pair(w, true);
+      int w = w0 + 1;
+      for (; w + 1 < Kw; w += 2) pair2(w);
+      if (w < Kw) pair(w, true);
       row_amb = !(slack > 0.0f);
     }
     if (__any_sync(0xffffffffu, row_amb)) {          // rare: redo the row with the exact division (set or clear each bit)
