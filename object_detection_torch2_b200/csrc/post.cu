@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
 
   NMS_TRACE(2);
   long long t_sweep = 0, t_matrix = 0, t_walk = 0, t_mark = p.trace != nullptr ? clock64() : 0;
+  long long t_load = 0, t_pairs = 0, t_xchg = 0, t_sub = 0;      // break-down of t_sweep (thread 0 of CTA 0)
   // ---- C. greedy suppression -----------------------------------------------------------------------------
   const ThrBand band = p.band;
   const PairThr pt = make_pair_thr(band.thr);
@@ -507,6 +508,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
     }
     const int kept_before = sh.kept;
     const int kept_local = kept_before > rank ? (kept_before - rank + kCl - 1) / kCl : 0;      // my share of the kept list
+    if (p.trace != nullptr && tid == 0 && trace_on) { t_sub = clock64(); t_load += t_sub - t_mark; }
     {
       // Fast sweep, no per-pair branch.  Per pair ONE value, e = inter * (1 + thr) - thr * (area_k + area_me) (the kept box's
       // thr * area is stored with it): mathematically inter - thr * union, whose sign decides IoU > thr.  Rounding (of e
@@ -554,6 +556,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
           }
         }
       }
+      NMS_ACC(t_pairs, t_sub);
 #pragma unroll
       for (int q = 0; q < kCand; ++q) {
         bool dead = acc[q] > m[q];
@@ -601,6 +604,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
       }
       __syncthreads();
     }
+    NMS_ACC(t_xchg, t_sub);
     int M = 0;
 #pragma unroll
     for (int w = 0; w < kTileWords; ++w) M += __popc(tile.alive_w[w]);
@@ -734,6 +738,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
   NMS_TRACE(3);
   if (p.trace != nullptr && tid == 0) {
     p.trace[trace_slot * 16 + 9] = t_sweep;
+    p.trace[trace_slot * 16 + 12] = t_load;
+    p.trace[trace_slot * 16 + 13] = t_pairs;
+    p.trace[trace_slot * 16 + 14] = t_xchg;
     p.trace[trace_slot * 16 + 10] = t_matrix;
     p.trace[trace_slot * 16 + 11] = t_walk;
   }
