@@ -240,8 +240,7 @@ struct NmsParams {
 };
 
 constexpr int kTileC = 256;                        // candidates settled per round of the greedy suppression
-constexpr int kCand = 2;                           // candidates per thread in the sweep over the kept list (register tile)
-constexpr int kSplit = kNmsThreads * kCand / kTileC;   // threads sharing one candidate group in that sweep
+constexpr int kSplit = kNmsThreads / kTileC;       // threads sharing one candidate in the sweep over the kept list
 constexpr int kTileWords = kTileC / 32;
 constexpr int kNmsCluster = 4;                    // CTAs (SMs) sharing a dense image: the kept list is dealt round-robin to them
 
@@ -301,13 +300,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
   uint16_t* idx_b = idx_a + Pp;
   uint16_t* whist = idx_b + Pp;                 // [32 warps][256 digits]
   // kept-list view (aliases the sort buffers, used after the order has been written to global memory)
-  // (entry g of the kept list lives in CTA g % kCl, so a CTA holds at most ceil(P / kCl) of them)
-  const size_t Pq = ((static_cast<size_t>(P) + kCl - 1) / kCl + 15) & ~static_cast<size_t>(15);
   float4* k_box = reinterpret_cast<float4*>(region);          // x1, x2, y1, y2
-  float* k_area = reinterpret_cast<float*>(k_box + Pq);
-  float* k_tarea = k_area + Pq;                               // thr * area: the kept box's share of the sweep's test
-  uint8_t* k_cls = reinterpret_cast<uint8_t*>(k_tarea + Pq);
-  const size_t sort_bytes = Pp * (4 + 4 + 2 + 2) + kNmsWarps * 256 * 2, kept_bytes = Pq * (16 + 4 + 4 + 1);
+  float* k_area = reinterpret_cast<float*>(k_box + Pp);
+  uint8_t* k_cls = reinterpret_cast<uint8_t*>(k_area + Pp);
+  const size_t sort_bytes = Pp * (4 + 4 + 2 + 2) + kNmsWarps * 256 * 2, kept_bytes = Pp * (16 + 4 + 1);
   NmsTile& tile = *reinterpret_cast<NmsTile*>(region + (((sort_bytes > kept_bytes ? sort_bytes : kept_bytes) + 15) & ~static_cast<size_t>(15)));
 
   // The grid is a few dozen clusters, each walking over the images cluster_id, cluster_id + n_clusters, ...; the flags of
@@ -458,7 +454,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
 
   NMS_TRACE(2);
   long long t_sweep = 0, t_matrix = 0, t_walk = 0, t_mark = p.trace != nullptr ? clock64() : 0;
-  long long t_load = 0, t_pairs = 0, t_xchg = 0, t_sub = 0;      // break-down of t_sweep (thread 0 of CTA 0)
   // ---- C. greedy suppression -----------------------------------------------------------------------------
   const ThrBand band = p.band;
   const PairThr pt = make_pair_thr(band.thr);
@@ -482,105 +477,66 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
   // (src/utils.py:102-108) at a few instructions per candidate; (4) the kept rows join the kept list.
   for (int base = 0; base < K; base += kTileC) {
     if (sh.stop) break;
-    // Thread (c, part) holds kCand candidates -- c, c + kTileC / kCand, ... -- in registers and tests every kept box it loads
-    // against all of them: the sweep is bound by the shared-memory pipe (a broadcast LDS.128 still delivers 512 bytes to the
-    // warp's registers), not by arithmetic, so the loads are what has to be shared; kSplit threads share a candidate group's
-    // sweep over the kept list.
     const int c = tid / kSplit, part = tid % kSplit;
-    bool alive[kCand];
-    int my_row[kCand], my_cls[kCand];
-    float4 me4[kCand];
-    float me_area[kCand];
-#pragma unroll
-    for (int q = 0; q < kCand; ++q) {
-      const int i = base + c + q * (kTileC / kCand);
-      alive[q] = i < K;
-      my_row[q] = 0; my_cls[q] = 0;
-      Corners me = {0.f, 0.f, 0.f, 0.f, 0.f};
-      if (alive[q]) {
-        my_row[q] = order[i];
-        const float* b = img + static_cast<size_t>(my_row[q]) * row;
-        me = make_corners(b[0], b[1], b[2], b[3]);
-        if (kPerClass) my_cls[q] = cls_in[my_row[q]];
-      }
-      me4[q] = make_float4(me.x1, me.x2, me.y1, me.y2);
-      me_area[q] = me.area;
+    const int i = base + c;
+    bool alive = i < K;
+    int my_row = 0, my_cls = 0;
+    Corners me = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (alive) {
+      my_row = order[i];
+      const float* b = img + static_cast<size_t>(my_row) * row;
+      me = make_corners(b[0], b[1], b[2], b[3]);
+      if (kPerClass) my_cls = cls_in[my_row];
     }
+    const float4 me4 = make_float4(me.x1, me.x2, me.y1, me.y2);
     const int kept_before = sh.kept;
     const int kept_local = kept_before > rank ? (kept_before - rank + kCl - 1) / kCl : 0;      // my share of the kept list
-    if (p.trace != nullptr && tid == 0 && trace_on) { t_sub = clock64(); t_load += t_sub - t_mark; }
     {
-      // Fast sweep, no per-pair branch.  Per pair ONE value, e = inter * (1 + thr) - thr * (area_k + area_me) (the kept box's
-      // thr * area is stored with it): mathematically inter - thr * union, whose sign decides IoU > thr.  Rounding (of e
-      // itself, of the reference's own union and of its quotient) moves that decision by less than
-      // (area_k + area_me) * (1 + thr) * 2^-19.  A kept box more than 2 / thr times the candidate's area cannot suppress it
-      // (IoU <= area_me / area_k) and its e is below -area_me / 2, so for every pair that matters the band is below
-      // m = area_me * (1 + 2 / thr) * (1 + thr) * 2^-18: max_k e_k > m means some kept box certainly suppresses the
-      // candidate, max_k e_k < -m means none does, and in between (a pair within ~1e-5 of the threshold) the candidate is
-      // settled with the IEEE division below; checked by brute force against the reference's fp32 arithmetic on 1e8 pairs at
-      // and around the threshold (tools/check_nms_band.py).  The verdict is a running maximum, and only ONE of the two
-      // extents is clamped at zero: with w clamped, a negative h makes inter <= 0 and e even more negative -- 11 arithmetic
-      // instructions per pair (round 1: 23, first pass of round 2: 16).  The test needs positive finite areas on both sides
-      // (odd boxes are flagged when they enter the kept list) and a threshold that is not tiny; otherwise: exact path.
-      const bool fast_ok = pt.usable && band.thr >= 1e-3f && sh.odd_kept == 0;
-      const float c1 = 1.0f + band.thr;
-      const float mk = c1 * (1.0f + __fdiv_rn(2.0f, band.thr)) * 3.814697265625e-06f;
-      bool tame[kCand];
-      float ntm[kCand], m[kCand], acc[kCand];
-#pragma unroll
-      for (int q = 0; q < kCand; ++q) {
-        tame[q] = fast_ok && me_area[q] >= 1e-30f && me_area[q] <= 1e30f;
-        ntm[q] = -(band.thr * me_area[q]);
-        m[q] = me_area[q] * mk;
-        acc[q] = -3.0e38f;
-      }
+      // fast sweep: no per-pair branch; the band test needs positive finite areas on both sides (odd boxes are flagged
+      // when they enter the kept list) and flags a borderline pair through `slack`; both cases redo the sweep exactly
+      const bool tame = pt.usable && sh.odd_kept == 0 && me.area >= 1e-30f && me.area <= 1e30f;
+      // Per pair two FMAs with exact signs: hi = inter - union * thr(1 + 2^-20), lo = inter - union * thr(1 - 2^-20).
+      // hi > 0: the rounded quotient is certainly above thr (suppressed); lo <= 0: certainly not; in between the pair is
+      // settled exactly below.  Both verdicts are accumulated as running maxima (no per-pair predicates), and only ONE of
+      // the two extents is clamped at zero: with w clamped, a negative h makes inter <= 0 and both values negative, the same
+      // verdict as the reference's doubly clamped product -- 16 instructions per pair instead of 23.
+      float acc_hi = -1.0f, acc_lo = -1.0f;
+      const float n_hi = -band.hi, n_lo = -band.lo;
       for (int j0 = 0; j0 < kept_local; j0 += 32 * kSplit) {
-        bool open = false;
-#pragma unroll
-        for (int q = 0; q < kCand; ++q) open = open || (alive[q] && !(acc[q] > m[q]));
-        if (!__any_sync(0xffffffffu, open)) break;
+        if (!__any_sync(0xffffffffu, alive && !(acc_hi > 0.0f))) break;
         const int j1 = min(j0 + 32 * kSplit, kept_local);
         int j = j0 + part;
 #pragma unroll 2
         for (; j < j1; j += kSplit) {
           const float4 kb = k_box[j];
-          const float kt = k_tarea[j];
-          const int kc = kPerClass ? k_cls[j] : 0;
-#pragma unroll
-          for (int q = 0; q < kCand; ++q) {
-            const float wd = fmaxf(fminf(kb.y, me4[q].y) - fmaxf(kb.x, me4[q].x), 0.0f);
-            const float ht = fminf(kb.w, me4[q].w) - fmaxf(kb.z, me4[q].z);
-            float e = fmaf(wd * ht, c1, ntm[q] - kt);
-            if (kPerClass) e = kc == my_cls[q] ? e : -3.0e38f;
-            acc[q] = fmaxf(acc[q], e);
+          const float wd = fmaxf(fminf(kb.y, me4.y) - fmaxf(kb.x, me4.x), 0.0f);
+          const float ht = fminf(kb.w, me4.w) - fmaxf(kb.z, me4.z);
+          const float inter = wd * ht;
+          const float uni = (k_area[j] + me.area) - inter;
+          float hi = fmaf(uni, n_hi, inter), lo = fmaf(uni, n_lo, inter);
+          if (kPerClass) { const bool same = k_cls[j] == my_cls; hi = same ? hi : -1.0f; lo = same ? lo : -1.0f; }
+          acc_hi = fmaxf(acc_hi, hi);
+          acc_lo = fmaxf(acc_lo, lo);
+        }
+      }
+      bool dead = acc_hi > 0.0f;
+      const bool maybe = acc_lo > 0.0f;
+      const bool redo = alive && (!tame || (maybe && !dead));
+      if (__any_sync(0xffffffffu, redo)) {     // rare: settle this candidate with the IEEE division
+        if (redo) {
+          dead = false;
+          for (int j = part; j < kept_local && !dead; j += kSplit) {
+            bool hit = suppresses(k_box[j], k_area[j], me4, me.area);
+            if (kPerClass) hit = hit && (k_cls[j] == my_cls);
+            dead = hit;
           }
         }
       }
-      NMS_ACC(t_pairs, t_sub);
-#pragma unroll
-      for (int q = 0; q < kCand; ++q) {
-        bool dead = acc[q] > m[q];
-        const bool maybe = !(acc[q] < -m[q]);
-        const bool redo = alive[q] && (!tame[q] || (maybe && !dead));
-        if (__any_sync(0xffffffffu, redo)) {     // rare: settle this candidate with the IEEE division
-          if (redo) {
-            dead = false;
-            for (int j = part; j < kept_local && !dead; j += kSplit) {
-              bool hit = suppresses(k_box[j], k_area[j], me4[q], me_area[q]);
-              if (kPerClass) hit = hit && (k_cls[j] == my_cls[q]);
-              dead = hit;
-            }
-          }
-        }
-        alive[q] = alive[q] && !dead;
-      }
+      alive = alive && !dead;
     }
 #pragma unroll
-    for (int q = 0; q < kCand; ++q) {
-#pragma unroll
-      for (int o = 1; o < kSplit; o <<= 1) alive[q] = (__shfl_xor_sync(0xffffffffu, alive[q] ? 1 : 0, o) != 0) && alive[q];
-      if (part == 0) tile.alive[c + q * (kTileC / kCand)] = alive[q] ? 1 : 0;
-    }
+    for (int o = 1; o < kSplit; o <<= 1) alive = (__shfl_xor_sync(0xffffffffu, alive ? 1 : 0, o) != 0) && alive;
+    if (part == 0) tile.alive[c] = alive ? 1 : 0;
     __syncthreads();
     if (warp < kTileWords) {
       const uint32_t w = __ballot_sync(0xffffffffu, tile.alive[32 * warp + lane] != 0);
@@ -603,23 +559,21 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
         tile.alive_w[tid] = a;
       }
       __syncthreads();
+      alive = alive && ((tile.alive_w[c >> 5] >> (c & 31)) & 1u) != 0u;
     }
-    NMS_ACC(t_xchg, t_sub);
-    int M = 0;
+    int M = 0, my_idx = 0;
 #pragma unroll
-    for (int w = 0; w < kTileWords; ++w) M += __popc(tile.alive_w[w]);
-    if (part == 0) {
-#pragma unroll
-      for (int q = 0; q < kCand; ++q) {
-        const int cq = c + q * (kTileC / kCand);
-        if (!((tile.alive_w[cq >> 5] >> (cq & 31)) & 1u)) continue;      // suppressed here or in a peer CTA
-        int my_idx = __popc(tile.alive_w[cq >> 5] & ((1u << (cq & 31)) - 1u));
-        for (int w = 0; w < (cq >> 5); ++w) my_idx += __popc(tile.alive_w[w]);
-        tile.box[my_idx] = me4[q];
-        tile.area[my_idx] = me_area[q];
-        tile.cls[my_idx] = static_cast<uint8_t>(my_cls[q]);
-        tile.row[my_idx] = my_row[q];
-      }
+    for (int w = 0; w < kTileWords; ++w) {
+      const uint32_t aw = tile.alive_w[w];
+      if (w < (c >> 5)) my_idx += __popc(aw);
+      else if (w == (c >> 5)) my_idx += __popc(aw & ((1u << (c & 31)) - 1u));
+      M += __popc(aw);
+    }
+    if (alive && part == 0) {
+      tile.box[my_idx] = me4;
+      tile.area[my_idx] = me.area;
+      tile.cls[my_idx] = static_cast<uint8_t>(my_cls);
+      tile.row[my_idx] = my_row;
     }
     __syncthreads();
     NMS_ACC(t_sweep, t_mark);
@@ -718,7 +672,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
           const int lp = pos / kCl;
           k_box[lp] = tile.box[tid];
           k_area[lp] = tile.area[tid];
-          k_tarea[lp] = band.thr * tile.area[tid];
           if (!(tile.area[tid] >= 1e-30f && tile.area[tid] <= 1e30f)) sh.odd_kept = 1;
           k_cls[lp] = tile.cls[tid];
         }
@@ -738,9 +691,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const NmsParams p, 
   NMS_TRACE(3);
   if (p.trace != nullptr && tid == 0) {
     p.trace[trace_slot * 16 + 9] = t_sweep;
-    p.trace[trace_slot * 16 + 12] = t_load;
-    p.trace[trace_slot * 16 + 13] = t_pairs;
-    p.trace[trace_slot * 16 + 14] = t_xchg;
     p.trace[trace_slot * 16 + 10] = t_matrix;
     p.trace[trace_slot * 16 + 11] = t_walk;
   }
@@ -1144,8 +1094,7 @@ static size_t nms_smem_bytes(int P) {
   const size_t Pp = (static_cast<size_t>(P) + 15) & ~static_cast<size_t>(15);
   const size_t head = ((sizeof(NmsShared) + 15) & ~static_cast<size_t>(15)) + ((static_cast<size_t>((P + 31) / 32) * 4 + 15) & ~static_cast<size_t>(15));
   const size_t sort_bytes = Pp * (4 + 4 + 2 + 2) + kNmsWarps * 256 * 2;
-  const size_t Pq = ((static_cast<size_t>(P) + kNmsCluster - 1) / kNmsCluster + 15) & ~static_cast<size_t>(15);
-  const size_t kept_bytes = Pq * (16 + 4 + 4 + 1);
+  const size_t kept_bytes = Pp * (16 + 4 + 1);
   return head + (((sort_bytes > kept_bytes ? sort_bytes : kept_bytes) + 15) & ~static_cast<size_t>(15)) + sizeof(NmsTile) + 16;
 }
 

@@ -17,4 +17,3 @@ for i, nm in enumerate(["A compaction", "B sort", "C greedy rounds"]):
     print(f"{nm:18s} median {np.median(t[:, i + 1] - t[:, i]):9.0f} cycles")
 for i, nm in zip((9, 10, 11), ("  sweep over kept list", "  bit matrix", "  walk + append")):
     print(f"{nm:22s} median {np.median(t[:, i]):9.0f} cycles")
-print("  sweep break-down (median): candidate loads %.0f, pair loop %.0f, exact redo + verdict exchange (block + cluster barriers) %.0f" % tuple(np.median(t[:, 12:15], axis=0)))
