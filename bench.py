@@ -761,6 +761,23 @@ def bench_pack(ctx):
         torch.cuda.synchronize()
         res[name] = e0.elapsed_time(e1) / (reps * len(sets))
     res["hbm_frac"] = n * 2 * SLAB / (res["ms"] * 1e-3) / 1e9 / peak
+    # the same pass for channels-last detector outputs (cuDNN's preferred layout): every (level, image) block is already in
+    # slab order, ssdh_pack_head_nhwc is a plain copy
+    for xs in sets:
+        for i, t in enumerate(xs):
+            xs[i] = t.contiguous(memory_format=torch.channels_last)
+    for xs in sets:
+        ops.pack_head(xs, ROW)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        for xs in sets:
+            ops.pack_head(xs, ROW)
+    e1.record()
+    torch.cuda.synchronize()
+    res["channels_last_ms"] = e0.elapsed_time(e1) / (10 * len(sets))
+    res["channels_last_hbm_frac"] = n * 2 * SLAB / (res["channels_last_ms"] * 1e-3) / 1e9 / peak
     return res
 
 

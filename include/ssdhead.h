@@ -188,6 +188,15 @@ SSDH_API int ssdh_pack_head(const float* const* levels, const int* ch, const int
 SSDH_API int ssdh_unpack_head(const float* grad_outputs, float* const* level_grads, const int* ch, const int* hw, int n_levels,
                               int N, int width, int P, ssdh_stream_t stream);
 
+/* The same two passes for channels-last producers: levels[k] / level_grads[k] are (N, hw[k], ch[k]) contiguous -- the memory of
+ * an (N, ch, H, W) tensor in torch.channels_last format, which is what cuDNN's tensor-core convolutions prefer to write.  Every
+ * (level, image) block is then already in slab order and the pass is a plain copy (permute(0, 2, 3, 1) is free, reshape + cat
+ * of src/model/ssd.py:103-104 is the copy). */
+SSDH_API int ssdh_pack_head_nhwc(const float* const* levels, const int* ch, const int* hw, int n_levels, int N, int width,
+                                 float* outputs, int P, ssdh_stream_t stream);
+SSDH_API int ssdh_unpack_head_nhwc(const float* grad_outputs, float* const* level_grads, const int* ch, const int* hw, int n_levels,
+                                   int N, int width, int P, ssdh_stream_t stream);
+
 /* SURVEY 8f-3 -- ground-truth ingest, the device side of collate_fn (src/utils.py:8-16): compact rows
  * [cx, cy, w, h, label] (N, G, 5) fp32 and the per-image row counts lengths[N] (NULL: every row is real) are expanded
  * into the dense zero-padded one-hot tensor targets (N, G, 4 + C) that pad_sequence would have produced.  label is a

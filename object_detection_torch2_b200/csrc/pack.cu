@@ -129,9 +129,85 @@ static int run_pack(float* const* levels, const int* ch, const int* hw, int n_le
   return cuda_status(fn);
 }
 
+// Channels-last producers.  A detector output in torch.channels_last format is (N, H*W, ch) in memory, so every (level,
+// image) block already IS the block of slab rows it belongs to: the pass is a plain copy of N * n_levels contiguous ranges,
+// one CTA per 4 096 floats of a range, in the widest requests the two addresses allow (16 / 8 / 4 bytes -- the slab offset of
+// a level is a multiple of 100 bytes, not of 16).
+constexpr int kCopyFloats = 4096;
+
+template <bool kUnpack>
+__global__ void __launch_bounds__(256) pack_head_nhwc_kernel(const PackParams p) {
+  const int n = blockIdx.y;
+  int t = blockIdx.x, l = 0;
+#pragma unroll
+  for (int q = 1; q < kPackMaxLevels; ++q) l += (q < p.n_levels && t >= p.tile_start[q]) ? 1 : 0;
+  t -= p.tile_start[l];
+  const size_t block = static_cast<size_t>(p.ch[l]) * p.hw[l];                      // floats of one (level, image) block
+  const size_t off = static_cast<size_t>(t) * kCopyFloats;
+  const int count = static_cast<int>(block - off < kCopyFloats ? block - off : kCopyFloats);
+  float* lev = p.level[l] + static_cast<size_t>(n) * block + off;
+  float* slab = p.slab + (static_cast<size_t>(n) * p.P + p.row_off[l]) * p.width + off;
+  const float* src = kUnpack ? slab : lev;
+  float* dst = kUnpack ? lev : slab;
+  const uintptr_t both = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst);
+  if ((both & 15u) == 0 && (count & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < count / 4; i += 256) d4[i] = s4[i];
+  } else if ((both & 7u) == 0 && (count & 1) == 0) {
+    const float2* s2 = reinterpret_cast<const float2*>(src);
+    float2* d2 = reinterpret_cast<float2*>(dst);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < count / 2; i += 256) d2[i] = s2[i];
+  } else {
+#pragma unroll 4
+    for (int i = threadIdx.x; i < count; i += 256) dst[i] = src[i];
+  }
+}
+
+static int run_pack_nhwc(float* const* levels, const int* ch, const int* hw, int n_levels, int N, int width, float* slab, int P,
+                         bool unpack, ssdh_stream_t stream, const char* fn) {
+  if (!levels || !ch || !hw || !slab || n_levels <= 0 || N <= 0 || width <= 0 || P <= 0) { set_error("%s: NULL pointer or non-positive dimension", fn); return SSDH_E_ARG; }
+  if (n_levels > kPackMaxLevels) { set_error("%s: at most %d levels (got %d)", fn, kPackMaxLevels, n_levels); return SSDH_E_LIMIT; }
+  if (N > 65535) { set_error("%s: N <= 65535", fn); return SSDH_E_LIMIT; }
+  PackParams p = {};
+  long long rows = 0;
+  int tiles = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!levels[l] || ch[l] <= 0 || hw[l] <= 0 || ch[l] % width != 0) {
+      set_error("%s: level %d: NULL pointer, empty shape or channel count %d not a multiple of the row width %d", fn, l, ch[l], width);
+      return SSDH_E_ARG;
+    }
+    p.level[l] = levels[l]; p.ch[l] = ch[l]; p.hw[l] = hw[l];
+    p.row_off[l] = static_cast<int>(rows);
+    rows += static_cast<long long>(hw[l]) * (ch[l] / width);
+    p.tile_start[l] = tiles;
+    tiles += static_cast<int>((static_cast<long long>(hw[l]) * ch[l] + kCopyFloats - 1) / kCopyFloats);
+  }
+  p.tile_start[n_levels] = tiles;
+  if (rows != P) { set_error("%s: the levels hold %lld rows, the slab %d", fn, rows, P); return SSDH_E_ARG; }
+  p.n_levels = n_levels; p.N = N; p.width = width; p.P = P; p.slab = slab;
+  const dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(N));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (unpack) pack_head_nhwc_kernel<true><<<grid, 256, 0, st>>>(p);
+  else pack_head_nhwc_kernel<false><<<grid, 256, 0, st>>>(p);
+  return cuda_status(fn);
+}
+
 }  // namespace ssdh
 
 using namespace ssdh;
+
+extern "C" int ssdh_pack_head_nhwc(const float* const* levels, const int* ch, const int* hw, int n_levels, int N, int width,
+                                   float* outputs, int P, ssdh_stream_t stream) {
+  return run_pack_nhwc(const_cast<float* const*>(reinterpret_cast<const float* const*>(levels)), ch, hw, n_levels, N, width, outputs, P, false, stream, "ssdh_pack_head_nhwc");
+}
+
+extern "C" int ssdh_unpack_head_nhwc(const float* grad_outputs, float* const* level_grads, const int* ch, const int* hw, int n_levels,
+                                     int N, int width, int P, ssdh_stream_t stream) {
+  return run_pack_nhwc(level_grads, ch, hw, n_levels, N, width, const_cast<float*>(grad_outputs), P, true, stream, "ssdh_unpack_head_nhwc");
+}
 
 extern "C" int ssdh_pack_head(const float* const* levels, const int* ch, const int* hw, int n_levels, int N, int width,
                               float* outputs, int P, ssdh_stream_t stream) {

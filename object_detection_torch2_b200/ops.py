@@ -318,38 +318,50 @@ def prefetch_l2(t: torch.Tensor) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ 8f-1 head producer
-def _pack_call(levels, slab, width, unpack):
+def _pack_call(levels, slab, width, unpack, nhwc=False):
     lib = _lib.load()
     n_levels = len(levels)
     N = slab.shape[0]
     ptrs = (ctypes.c_void_p * n_levels)(*[t.data_ptr() for t in levels])
     ch = (ctypes.c_int * n_levels)(*[t.shape[1] for t in levels])
     hw = (ctypes.c_int * n_levels)(*[t.shape[2] * t.shape[3] for t in levels])
+    sfx = "_nhwc" if nhwc else ""
     with torch.cuda.device(slab.device):
         if unpack:
-            check(lib.ssdh_unpack_head(slab.data_ptr(), ptrs, ch, hw, n_levels, N, width, slab.shape[1], _stream()), "ssdh_unpack_head")
+            check(getattr(lib, "ssdh_unpack_head" + sfx)(slab.data_ptr(), ptrs, ch, hw, n_levels, N, width, slab.shape[1], _stream()), "ssdh_unpack_head" + sfx)
         else:
-            check(lib.ssdh_pack_head(ptrs, ch, hw, n_levels, N, width, slab.data_ptr(), slab.shape[1], _stream()), "ssdh_pack_head")
+            check(getattr(lib, "ssdh_pack_head" + sfx)(ptrs, ch, hw, n_levels, N, width, slab.data_ptr(), slab.shape[1], _stream()), "ssdh_pack_head" + sfx)
+
+
+def _channels_last(t: torch.Tensor) -> bool:
+    """The tensor's memory is (N, H*W, C): torch.channels_last (a 1 x 1 map is both layouts at once)."""
+    return t.dtype == torch.float32 and t.is_contiguous(memory_format=torch.channels_last)
 
 
 class _PackHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, width, *levels):
-        levels = [_f32c(t) for t in levels]
         _need_cuda(*levels)
+        # channels-last producers (what cuDNN's tensor-core convolutions write): every (level, image) block is already in slab
+        # order, the pass is a plain copy; otherwise NCHW, the transposing kernel
+        nhwc = all(_channels_last(t) for t in levels)
+        if not nhwc:
+            levels = [_f32c(t) for t in levels]
         N = levels[0].shape[0]
         rows = sum(t.shape[1] // width * t.shape[2] * t.shape[3] for t in levels)
         out = torch.empty((N, rows, width), dtype=torch.float32, device=levels[0].device)
-        _pack_call(levels, out, width, unpack=False)
+        _pack_call(levels, out, width, unpack=False, nhwc=nhwc)
         ctx.width = width
         ctx.shapes = [t.shape for t in levels]
+        ctx.nhwc = nhwc
         return out
 
     @staticmethod
     def backward(ctx, grad):
         grad = _f32c(grad)
-        grads = [torch.empty(s, dtype=torch.float32, device=grad.device) for s in ctx.shapes]
-        _pack_call(grads, grad, ctx.width, unpack=True)
+        fmt = torch.channels_last if ctx.nhwc else torch.contiguous_format
+        grads = [torch.empty(s, dtype=torch.float32, device=grad.device, memory_format=fmt) for s in ctx.shapes]
+        _pack_call(grads, grad, ctx.width, unpack=True, nhwc=ctx.nhwc)
         return (None, *grads)
 
 

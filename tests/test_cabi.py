@@ -37,6 +37,9 @@ def test_library_exports_header_symbols():
     assert lib.ssdh_pack_head(ptrs, ch, hw, 1, 1, 25, 1, 9, None) == -1 and b"rows" in lib.ssdh_last_error()
     assert lib.ssdh_pack_head(ptrs, ch, hw, 9, 1, 25, 1, 8, None) == -2          # SSDH_E_LIMIT: more than 8 levels
     assert lib.ssdh_unpack_head(None, None, None, None, 1, 1, 25, 1, None) == -1
+    assert lib.ssdh_pack_head_nhwc(None, None, None, 1, 1, 25, None, 1, None) == -1
+    assert lib.ssdh_pack_head_nhwc(ptrs, ch, hw, 1, 1, 25, 1, 9, None) == -1 and b"rows" in lib.ssdh_last_error()
+    assert lib.ssdh_unpack_head_nhwc(None, None, None, None, 1, 1, 25, 1, None) == -1
     assert lib.ssdh_expand_targets(None, None, 2, 3, 21, None, None) == -1
     assert lib.ssdh_expand_targets(None, None, 0, 3, 21, None, None) == 0         # nothing to do
     # round-2 entry points: kept-list evaluation, VOC AP, extended loss, scalar exchange

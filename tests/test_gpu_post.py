@@ -252,6 +252,29 @@ def test_pack_head_matches_permute_reshape_cat(n, width, levels):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,width,levels", [(3, 25, SSD_LEVELS), (2, 9, [(7, 3), (2, 1), (33, 2)]), (5, 7, [(3, 1), (4, 5)])])
+def test_pack_head_channels_last_producers(n, width, levels):
+    """Detector outputs in torch.channels_last format (what cuDNN's tensor-core convolutions write) take the copy path
+    (ssdh_pack_head_nhwc / ssdh_unpack_head_nhwc): same values as the reference tail, gradients in channels_last too."""
+    g = torch.Generator().manual_seed(n * 1000 + width)
+    xs = [torch.randn(n, a * width, m, m, generator=g).to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for m, a in levels]
+    assert all(x.is_contiguous(memory_format=torch.channels_last) for x in xs)
+    out = ops.pack_head(xs, width)
+    want = _reference_tail([x.detach() for x in xs], width)
+    assert out.shape == want.shape and torch.equal(out, want)
+    w = torch.randn(out.shape, generator=g).to(DEV)
+    (out * w).sum().backward()
+    ys = [x.detach().clone().requires_grad_(True) for x in xs]
+    (_reference_tail(ys, width) * w).sum().backward()
+    for x, y in zip(xs, ys):
+        assert torch.equal(x.grad, y.grad)
+        assert x.grad.is_contiguous(memory_format=torch.channels_last)
+    # a mixed list (one level NCHW) falls back to the transposing kernel and still agrees
+    mixed = [x.detach() if i else x.detach().contiguous() for i, x in enumerate(xs)]
+    assert torch.equal(ops.pack_head(mixed, width), want)
+
+
+@pytest.mark.gpu
 def test_pack_head_rejects_bad_shapes():
     x = torch.zeros(2, 26, 3, 3, device=DEV)
     with pytest.raises(ValueError):

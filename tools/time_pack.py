@@ -8,7 +8,9 @@ LEVELS = [(38, 4), (19, 6), (10, 6), (5, 6), (3, 4), (1, 4)]
 ROT = max(2, 512 // N)
 sets = [[torch.randn(N, a * 25, m, m, device=dev) for m, a in LEVELS] for _ in range(ROT)]
 def ref(xs): return torch.cat([t.permute(0, 2, 3, 1).reshape(N, -1, 25) for t in xs], dim=1)
-for name, fn in (("ssdh_pack_head", lambda xs: ops.pack_head(xs, 25)), ("permute+reshape+cat", ref)):
+sets_cl = [[t.contiguous(memory_format=torch.channels_last) for t in xs] for xs in sets]
+for name, fn, sets in (("ssdh_pack_head", lambda xs: ops.pack_head(xs, 25), sets), ("permute+reshape+cat", ref, sets),
+                       ("ssdh_pack_head (channels-last inputs)", lambda xs: ops.pack_head(xs, 25), sets_cl), ("permute+reshape+cat (channels-last inputs)", ref, sets_cl)):
     for xs in sets: fn(xs)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
